@@ -1,0 +1,203 @@
+/*
+ * mellon_b200 — C ABI of the B200-native sparse-GP density hot path.
+ *
+ * The reference (settylab/Mellon v1.7.1) is pure Python/JAX and has no FFI of its own;
+ * its boundary for this path is a set of Python call sites.  Every entry point below
+ * names the reference call site(s) it replaces (paths relative to
+ * /root/reference/mellon).  INTEGRATION.md shows the ctypes stub a Mellon maintainer
+ * would add at each of those sites.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, doubles.  No torch / CUDA types in any signature.
+ *   - all matrices are float64, row-major, C-contiguous (ld == cols); a vector is an
+ *     (n, 1) matrix.
+ *   - `mb_mat` is an opaque handle to a device-resident matrix owned by a context.
+ *   - host pointers are caller-owned; the library copies (pinned staging inside).
+ *   - return code: 0 ok; <0 error (text via mb_last_error()); >0 only from the
+ *     Cholesky entry points = LAPACK-style `info` (1-based index of the first
+ *     non-positive pivot) — the host raises the reference's ValueError
+ *     (decomposition.py:116-122) on it.
+ *   - one context drives ONE GPU; one process per GPU.  With a communicator attached
+ *     (mb_comm_init) the cell axis is sharded across ranks (each rank holds a block of
+ *     rows of x / K_NM / L) and the entry points marked [all-reduce] sum their result
+ *     over ranks with NCCL (sum, f64, on the device) before returning it, so every
+ *     rank sees identical bits.
+ */
+#ifndef MELLON_B200_H
+#define MELLON_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mb_ctx mb_ctx;
+typedef struct mb_mat mb_mat;
+
+/* ---- covariance program ------------------------------------------------------------
+ * A covariance expression (cov.py kernels combined with base_cov.py Add/Mul/Pow and
+ * nested active_dims) is flattened on the host into a postfix program.  Leaves carry
+ * ABSOLUTE column indices into the input matrix (nested active_dims already composed,
+ * base_cov.py:310-315, util.py:150-171). */
+enum mb_kernel_kind {          /* leaf kinds: cov.py                                  */
+  MB_K_MATERN32 = 0,           /* cov.py:62-66    r=sqrt(3) d/ls ; (r+1) e^-r          */
+  MB_K_MATERN52 = 1,           /* cov.py:157-161  r=sqrt(5) d/ls ; (r+r^2/3+1) e^-r    */
+  MB_K_EXPQUAD = 2,            /* cov.py:255-259  exp(-(d/ls)^2/2)                     */
+  MB_K_EXPONENTIAL = 3,        /* cov.py:352-356  exp(-(d/ls)/2)                       */
+  MB_K_RATQUAD = 4,            /* cov.py:453-457  ((d/ls)^2/(2a)+1)^-a                 */
+  MB_K_LINEAR = 5,             /* cov.py:551-556  x.y/ls                               */
+  MB_K_DISTANCE = 6            /* util.py:351-366 the bare distance (ls unused)        */
+};
+enum mb_kop_code {
+  MB_OP_LEAF = 0,              /* push leaf value                                      */
+  MB_OP_CONST = 1,             /* push scalar `value`   (scalar right operand)         */
+  MB_OP_ADD = 2,               /* base_cov.py:309-315                                  */
+  MB_OP_MUL = 3,               /* base_cov.py:375-381                                  */
+  MB_OP_POW = 4                /* base_cov.py:449-453  top ** value                    */
+};
+typedef struct mb_kop {
+  int32_t op;                  /* mb_kop_code                                          */
+  int32_t kind;                /* mb_kernel_kind (LEAF only)                           */
+  double ls;                   /* length scale (LEAF)                                  */
+  double alpha;                /* RatQuad alpha (LEAF)                                 */
+  double value;                /* CONST value / POW exponent                           */
+  int32_t dim_off;             /* LEAF: offset into mb_kprog.dims                      */
+  int32_t dim_cnt;             /* LEAF: number of active columns; -1 = all columns     */
+} mb_kop;
+typedef struct mb_kprog {
+  int32_t n_ops;
+  int32_t n_dims;
+  const mb_kop* ops;
+  const int32_t* dims;
+} mb_kprog;
+
+#define MB_MAX_LEAVES 4
+#define MB_MAX_OPS 16
+#define MB_STACK_DEPTH 4
+
+/* ---- context / errors ---------------------------------------------------------------- */
+const char* mb_last_error(void);
+int mb_version(void);
+int mb_device_count(int* n);
+int mb_ctx_create(int device, mb_ctx** out);
+int mb_ctx_destroy(mb_ctx* ctx);
+int mb_ctx_sync(mb_ctx* ctx);
+int mb_ctx_info(mb_ctx* ctx, int* device, int* n_sm, int64_t* free_bytes, int64_t* total_bytes);
+/* number of this library's kernels launched through the context since creation */
+int64_t mb_ctx_launch_count(mb_ctx* ctx);
+/* device-side stopwatch on the context's stream (CUDA events): start / stop -> ms.
+ * `slot` in [0, 16) lets several intervals be open at once. */
+int mb_timer_start(mb_ctx* ctx, int slot);
+int mb_timer_stop(mb_ctx* ctx, int slot, double* ms);
+/* overwrite a scratch buffer larger than L2 (cache flush between timed iterations) */
+int mb_flush_l2(mb_ctx* ctx);
+/* select kernel variants for A/B measurements ("gemm", "cov", "lossgrad") */
+int mb_set_option(mb_ctx* ctx, const char* key, int value);
+
+/* pinned (page-locked) host buffers, so uploads / the streaming predictor overlap with compute */
+int mb_host_alloc(int64_t bytes, void** out);
+int mb_host_free(void* p);
+
+/* ---- communicator (NCCL over NVLink, one rank per process/GPU) ----------------------- */
+int mb_comm_unique_id(unsigned char* out128);
+int mb_comm_init(mb_ctx* ctx, const unsigned char* id128, int rank, int world);
+int mb_comm_destroy(mb_ctx* ctx);
+int mb_comm_info(mb_ctx* ctx, int* rank, int* world);
+/* sum a device matrix over ranks in place (no-op without a communicator) */
+int mb_comm_allreduce(mb_ctx* ctx, mb_mat* a);
+/* gather equally-sized row blocks: out(world*rows, cols) <- a(rows, cols) of each rank */
+int mb_comm_allgather(mb_ctx* ctx, const mb_mat* a, mb_mat* out);
+
+/* ---- device matrices ------------------------------------------------------------------ */
+int mb_mat_alloc(mb_ctx* ctx, int64_t rows, int64_t cols, mb_mat** out);
+int mb_mat_free(mb_ctx* ctx, mb_mat* m);
+int mb_mat_shape(const mb_mat* m, int64_t* rows, int64_t* cols);
+/* copy `nrows` full rows starting at device row `row0` from / to a host buffer */
+int mb_mat_upload(mb_ctx* ctx, mb_mat* m, const double* host, int64_t row0, int64_t nrows);
+int mb_mat_download(mb_ctx* ctx, const mb_mat* m, double* host, int64_t row0, int64_t nrows);
+int mb_mat_copy(mb_ctx* ctx, const mb_mat* src, mb_mat* dst);
+int mb_mat_fill(mb_ctx* ctx, mb_mat* m, double v);
+/* dst(cols, rows) <- src(rows, cols)^T */
+int mb_mat_transpose(mb_ctx* ctx, const mb_mat* src, mb_mat* dst);
+/* A += v * I                      util.py:269-293 (stabilize / add_diagonal) */
+int mb_mat_add_diag(mb_ctx* ctx, mb_mat* a, double v);
+/* a(i, j) *= s(j)                 decomposition.py:265 (`* sqrt(S)`), inference.py:372 */
+int mb_mat_scale_cols(mb_ctx* ctx, mb_mat* a, const mb_mat* s);
+/* dst <- src[:, c0:c0+ncols]      decomposition.py:75-76 (`v[:, -p:]`) */
+int mb_mat_copy_cols(mb_ctx* ctx, const mb_mat* src, int64_t c0, int64_t ncols, mb_mat* dst);
+/* copy the lower triangle onto the upper one (symmetrise a lower-only result) */
+int mb_mat_symmetrize(mb_ctx* ctx, mb_mat* a);
+
+/* ---- K1: fused pairwise distance + covariance kernel -----------------------------------
+ * K(i, j) = prog(x_i, y_j); replaces util.py:351-366 (distance) + cov.py `k` methods +
+ * base_cov.py Add/Mul/Pow.k, i.e. every `cov_func(x, y)` call on the path
+ * (decomposition.py:114,199,255-256; conditional.py:237,514,370,655,903). */
+int mb_cov_build(mb_ctx* ctx, const mb_kprog* prog, const mb_mat* x, const mb_mat* y, mb_mat* K);
+/* diag(i) = prog(x_i, x_i)        base_cov.py:71-93 */
+int mb_cov_diag(mb_ctx* ctx, const mb_kprog* prog, const mb_mat* x, mb_mat* out);
+
+/* ---- K7: fused covariance + mat-vec (never materialises K) -----------------------------
+ * out = mu + prog(xq, base) @ w ; w is (m, p), out is (nq, p).
+ * Replaces `_mean` of the three conditionals: conditional.py:366-373, 651-658, 899-906. */
+int mb_cov_matvec(mb_ctx* ctx, const mb_kprog* prog, const mb_mat* xq, const mb_mat* base,
+                  const mb_mat* w, double mu, mb_mat* out);
+/* same with HOST queries / results, streamed through the device in double-buffered
+ * chunks (base_predictor.py:180-257 `Predictor.mean` body). */
+int mb_predict_mean(mb_ctx* ctx, const mb_kprog* prog, const double* xq_host, int64_t nq,
+                    int64_t d, const mb_mat* base, const mb_mat* w, double mu, double* out_host);
+
+/* ---- K2 / K3: Cholesky and triangular solves -------------------------------------------- */
+/* in-place lower Cholesky of a symmetric matrix (lower triangle read; strict upper
+ * zeroed).  Returns info > 0 on a non-positive pivot.  decomposition.py:115,
+ * conditional.py:63,73. */
+int mb_potrf(mb_ctx* ctx, mb_mat* a);
+/* Lp = chol(prog(xu, xu) + diag_add * I)      decomposition.py:79-123 (`_full_rank`) */
+int mb_cov_chol(mb_ctx* ctx, const mb_kprog* prog, const mb_mat* xu, double diag_add, mb_mat* Lp);
+/* X <- X Lp^-T  (X is n x m, rows independent)  decomposition.py:209
+ * `solve_triangular(Lp, C.T, lower=True).T`, conditional.py:519 */
+int mb_trsm_right_lt(mb_ctx* ctx, const mb_mat* Lp, mb_mat* X);
+/* B <- Lp^-1 B (trans=0) or Lp^-T B (trans=1), B is (m, nrhs)
+ * conditional.py:64-65,264,818 ; sklearn Ridge posv (parameters.py:896). */
+int mb_tri_solve(mb_ctx* ctx, const mb_mat* Lp, int trans, mb_mat* B);
+/* L = prog(x, xu) Lp^-T in one call   decomposition.py:174-210 (`_standard_low_rank`) */
+int mb_lowrank_standard(mb_ctx* ctx, const mb_kprog* prog, const mb_mat* x, const mb_mat* xu,
+                        const mb_mat* Lp, mb_mat* L);
+
+/* ---- K4: Gram contraction over the cell axis ------------------------------------------- */
+/* G = L^T L (r x r, full symmetric)  [all-reduce]
+ * parameters.py:896 (Ridge normal equations), conditional.py:61 (A A^T),
+ * decomposition.py:259 (QR of K_NM via its Gram). */
+int mb_gram(mb_ctx* ctx, const mb_mat* L, mb_mat* G);
+/* b = L^T t (r x 1)  [all-reduce]   parameters.py:896, conditional.py:64 (`dot(A, r_l)`) */
+int mb_gemv_t(mb_ctx* ctx, const mb_mat* L, const mb_mat* t, mb_mat* b);
+/* z0 = (L^T L + I)^-1 L^T t  [all-reduce inside]   parameters.py:877-896 */
+int mb_ridge_init(mb_ctx* ctx, const mb_mat* L, const mb_mat* t, double* z0_host);
+/* C = alpha op(A) op(B) + beta C ; op = transpose when the flag is 1 (local, no reduce) */
+int mb_gemm(mb_ctx* ctx, int trans_a, int trans_b, double alpha, const mb_mat* A,
+            const mb_mat* B, double beta, mb_mat* C);
+
+/* ---- K5 / K6: MAP objective ---------------------------------------------------------------
+ * One fused pass over the local rows of L:
+ *   f = L z + mu ; A = exp(f + V)
+ *   loss = 1/2 |z|^2 + (k/2) log 2pi - (sum_i (f_i - A_i) + sum_vdr)
+ *   grad = z + L^T (A - 1)                                     [all-reduce of r+1 doubles]
+ * inference.py:35-48, 51-69, 72-92, 167-192 + jax.value_and_grad (inference.py:285).
+ * `V` is the per-cell vector of inference.py:84; `sum_vdr` the global sum of :85. */
+int mb_loss_grad(mb_ctx* ctx, const mb_mat* L, const mb_mat* V, double sum_vdr, double mu,
+                 double k, const double* z_host, double* loss, double* grad_host);
+/* f = L z + mu for the local rows    inference.py:66-67, 341-354 */
+int mb_transform(mb_ctx* ctx, const mb_mat* L, const double* z_host, double mu, double* f_host);
+/* diag(I + L^T diag(A) L)  [all-reduce]   inference.py:311-317 in closed form */
+int mb_hess_diag(mb_ctx* ctx, const mb_mat* L, const mb_mat* V, double mu, const double* z_host,
+                 double* diag_host);
+
+/* ---- symmetric eigen-decomposition (Nystroem paths) -------------------------------------
+ * a <- eigenvectors (columns, ascending eigenvalues in w).  decomposition.py:50
+ * (`eigh`).  Jacobi-free: tridiagonalisation is hand-written; see DESIGN.md. */
+int mb_syevd(mb_ctx* ctx, mb_mat* a, mb_mat* w);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

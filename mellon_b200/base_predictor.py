@@ -1,0 +1,270 @@
+"""Predictor shells (``mellon/base_predictor.py``): input validation, normalisation,
+serialisation.  The arithmetic (``_mean`` etc.) lives in :mod:`mellon_b200.conditional` and
+runs on the GPU.
+"""
+
+from __future__ import annotations
+
+import bz2
+import gzip
+import json
+import logging
+import sys
+from abc import ABC, abstractmethod
+from datetime import datetime
+from importlib import import_module
+from typing import List, Set, Union
+
+import numpy as np
+from packaging import version
+
+from .base_cov import Covariance
+from .util import deserialize, ensure_2d, make_multi_time_argument, make_serializable, object_html, object_str
+from .validation import validate_array, validate_bool, validate_time_x
+
+logger = logging.getLogger("mellon")
+
+
+def _feature_error(expected, got):
+    return ValueError(
+        f"The predictor was trained on data with {expected} features. "
+        f"However, the provided input data has {got} features. "
+        "Please ensure that the input data has the same number of features as the training data."
+    )
+
+
+class Predictor(ABC):
+    """Callable posterior-mean predictor (``base_predictor.py:41-734``)."""
+
+    n_input_features: int
+    n_obs: int
+    d: int = None
+    d_method: str = None
+    _state_variables: Union[Set, List]
+
+    @abstractmethod
+    def __init__(self):
+        """Subclasses set cov_func, weights, mu, n_input_features, n_obs, _state_variables."""
+
+    def __str__(self):
+        return self.__repr__()
+
+    def __repr__(self):
+        n_obs = "None" if self.n_obs is None else f"{self.n_obs:,}"
+        rows = "\n".join(str(k) + ": " + object_str(v) for k, v in self._data_dict().items())
+        return (
+            f'A predictor of class "{self.__class__.__name__}" with covariance function '
+            f'"{self.cov_func!r}" trained on {n_obs} observations '
+            f"with {self.n_input_features:,} features and data:\n{rows}"
+        )
+
+    def _repr_html_(self):
+        n_obs = "None" if self.n_obs is None else f"{self.n_obs:,}"
+        rows = "".join(f"<tr><td>{k}</td><td>{object_html(v)}</td></tr>" for k, v in self._data_dict().items())
+        return (
+            f"<div><h3>Predictor: {self.__class__.__name__}</h3><p>Covariance: {self.cov_func!r}; "
+            f"{n_obs} observations; {self.n_input_features:,} features</p>"
+            f"<table><tr><th>Attribute</th><th>Value</th></tr>{rows}</table></div>"
+        )
+
+    # -- evaluation -----------------------------------------------------------------------------
+    @abstractmethod
+    def _mean(self, *args, **kwargs):
+        """Posterior mean at validated inputs."""
+
+    def _check_x(self, x):
+        x = ensure_2d(validate_array(x, "x"))
+        if x.shape[1] != self.n_input_features:
+            raise _feature_error(self.n_input_features, x.shape[1])
+        return x
+
+    def _normalisation_notes(self, what="samples/cells"):
+        if self.n_obs is None or self.n_obs == 0:
+            message = (
+                f"Cannot normalize without n_obs. Please set self.n_obs to the number "
+                f"of {what} trained on to enable normalization."
+            )
+            logger.error(message)
+            raise ValueError(message)
+        if self.d_method == "manual":
+            logger.info(
+                f"Using normalization with manually set d={self.d}. "
+                "Note: Normalization is most effective when d approximates the intrinsic dimensionality of the data."
+            )
+        elif self.d_method == "embedding" or (
+            self.d_method is None and isinstance(self.d, (int, float)) and float(self.d).is_integer()
+        ):
+            logger.warning(
+                f"The normalization is only effective if d approximates the intrinsic dimensionality. "
+                f"Current values: d_method={self.d_method}, d={self.d}. "
+                f'Consider using d_method="fractal" for more accurate results.'
+            )
+
+    def mean(self, x, normalize=False):
+        """Posterior mean at ``x`` (``base_predictor.py:180-255``); ``normalize`` subtracts
+        ``log(n_obs)``."""
+        x = self._check_x(x)
+        normalize = validate_bool(normalize, "normalize")
+        if normalize:
+            self._normalisation_notes()
+            return self._mean(x) - np.log(self.n_obs)
+        return self._mean(x)
+
+    __call__ = mean
+
+    @abstractmethod
+    def _covariance(self, *args, **kwargs):
+        """Posterior covariance of the GP at validated inputs."""
+
+    @abstractmethod
+    def _mean_covariance(self, *args, **kwargs):
+        """Covariance of the mean induced by parameter uncertainty."""
+
+    def covariance(self, x, diag=True, noise_free=False):
+        return self._covariance(self._check_x(x), diag=diag)
+
+    def mean_covariance(self, x, diag=True):
+        return self._mean_covariance(self._check_x(x), diag=diag)
+
+    def uncertainty(self, x, diag=True):
+        x = self._check_x(x)
+        return self._covariance(x, diag=diag) + self._mean_covariance(x, diag=diag)
+
+    def _data_dict(self):
+        return {key: getattr(self, key) for key in self._state_variables}
+
+    # -- serialisation (wire format of base_predictor.py:541-734) ------------------------------
+    def __getstate__(self):
+        module_name = self.__class__.__module__
+        meta = import_module(module_name.split(".")[0])
+        data = self._data_dict()
+        data.update(
+            {
+                "n_input_features": self.n_input_features,
+                "n_obs": self.n_obs,
+                "d": self.d,
+                "d_method": self.d_method,
+                "_state_variables": self._state_variables,
+            }
+        )
+        return {
+            "data": {k: make_serializable(v) for k, v in data.items()},
+            "cov_func": self.cov_func.__getstate__(),
+            "metadata": {
+                "classname": self.__class__.__name__,
+                "module_name": module_name,
+                "module_version": getattr(meta, "__version__", "NA"),
+                "serialization_date": datetime.now().isoformat(),
+                "python_version": sys.version,
+            },
+        }
+
+    def __setstate__(self, state):
+        for name, value in state["data"].items():
+            setattr(self, name, deserialize(value))
+        self.cov_func = Covariance.from_dict(state["cov_func"])
+
+    def copy(self):
+        new = self.__class__.__new__(self.__class__)
+        new.__setstate__(self.__getstate__())
+        return new
+
+    def to_dict(self):
+        return self.__getstate__()
+
+    def to_json(self, filename=None, compress=None):
+        json_str = json.dumps(self.to_dict())
+        if filename is None:
+            return json_str
+        if compress == "gzip":
+            if isinstance(filename, str) and not filename.endswith(".gz"):
+                filename += ".gz"
+            with gzip.open(filename, "wt") as f:
+                f.write(json_str)
+        elif compress == "bz2":
+            if isinstance(filename, str) and not filename.endswith(".bz2"):
+                filename += ".bz2"
+            with bz2.open(filename, "wt") as f:
+                f.write(json_str)
+        elif compress is None:
+            with open(filename, "w") as f:
+                f.write(json_str)
+        else:
+            msg = f'Unknown compression format {compress}.\nAvailabe formats are "gzip", "bz2" and None.'
+            logger.error(msg)
+            raise ValueError(msg)
+        logger.info(f"Written predictor to {filename}.")
+
+    @classmethod
+    def from_json(cls, filepath, compress=None):
+        name = str(filepath)
+        if compress == "gzip" or name.endswith(".gz"):
+            opener = gzip.open
+        elif compress == "bz2" or name.endswith(".bz2"):
+            opener = bz2.open
+        else:
+            opener = open
+        with opener(filepath, "rt") as f:
+            return cls.from_json_str(f.read())
+
+    @classmethod
+    def from_json_str(cls, json_str):
+        return cls.from_dict(json.loads(json_str))
+
+    @classmethod
+    def from_dict(cls, data_dict):
+        meta = data_dict["metadata"]
+        clsname, module_name = meta["classname"], meta["module_name"]
+        try:
+            old = version.parse(str(meta["module_version"])) < version.parse("1.4.0")
+        except version.InvalidVersion:
+            old = False
+        if old and module_name.startswith("mellon."):
+            logger.warning(
+                f"Loading a predictor written by mellon {meta['module_version']} < 1.4.0. "
+                "Please set predictor.n_obs to enable normalization."
+            )
+            clsname = clsname.replace("ConditionalMean", "Conditional")
+            data = data_dict["data"]
+            data["n_obs"] = data.get("n_obs", None)
+            data["_state_variables"] = data.get("_state_variables", set(data.keys()) - {"n_input_features"})
+        # predictors written by the reference name its module ("mellon.conditional"): same classes here
+        from . import conditional
+
+        Sub = getattr(conditional, clsname, None)
+        if Sub is None:
+            Sub = getattr(import_module(module_name), clsname)
+        instance = Sub.__new__(Sub)
+        instance.__setstate__(data_dict)
+        return instance
+
+
+class PredictorTime(Predictor):
+    """Predictor whose last input column is time (``base_predictor.py:852-1194``)."""
+
+    def _check_time_x(self, Xnew, time):
+        return validate_time_x(Xnew, time, n_features=self.n_input_features, cast_scalar=True)
+
+    @make_multi_time_argument
+    def mean(self, Xnew, time=None, normalize=False):
+        Xnew = self._check_time_x(Xnew, time)
+        normalize = validate_bool(normalize, "normalize")
+        if normalize:
+            self._normalisation_notes("samples/cells (per time point)")
+            return self._mean(Xnew) - np.log(self.n_obs)
+        return self._mean(Xnew)
+
+    __call__ = mean
+
+    @make_multi_time_argument
+    def covariance(self, Xnew, time=None, diag=True):
+        return self._covariance(self._check_time_x(Xnew, time), diag=diag)
+
+    @make_multi_time_argument
+    def mean_covariance(self, Xnew, time=None, diag=True):
+        return self._mean_covariance(self._check_time_x(Xnew, time), diag=diag)
+
+    @make_multi_time_argument
+    def uncertainty(self, Xnew, time=None, diag=True):
+        Xnew = self._check_time_x(Xnew, time)
+        return self._covariance(Xnew, diag=diag) + self._mean_covariance(Xnew, diag=diag)

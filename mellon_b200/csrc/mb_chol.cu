@@ -1,0 +1,244 @@
+// K2 / K3: recursive blocked Cholesky, right-side triangular solve (X <- X Lp^-T) and
+// vector triangular solves, all float64.  The O(n^3) work runs in the DMMA GEMM
+// (mb_gemm.cu); the kernels here are the 32-wide leaves.
+#include "mb_common.cuh"
+
+namespace {
+
+constexpr int NB = 32;
+
+// ---- leaf: Cholesky of one (w <= 32) diagonal block, one warp ------------------------------
+__global__ void potrf_leaf_kernel(double* __restrict__ A, int64_t lda, int w, int64_t global_off, int* info) {
+  __shared__ double S[NB][NB + 1];
+  const int lane = threadIdx.x;
+  for (int r = 0; r < w; r++)
+    if (lane < w) S[r][lane] = A[r * lda + lane];
+  __syncwarp();
+  for (int j = 0; j < w; j++) {
+    double d = S[j][j];
+    if (!(d > 0.0)) {
+      if (lane == 0) atomicCAS(info, 0, (int)(global_off + j + 1));
+      d = nan("");
+    }
+    d = sqrt(d);
+    __syncwarp();
+    if (lane == j) S[j][j] = d;
+    if (lane > j && lane < w) S[lane][j] = S[lane][j] / d;
+    __syncwarp();
+    if (lane > j && lane < w) {
+      const double lij = S[lane][j];
+      for (int k = j + 1; k <= lane; k++) S[lane][k] = fma(-lij, S[k][j], S[lane][k]);
+    }
+    __syncwarp();
+  }
+  for (int r = 0; r < w; r++)
+    if (lane < w) A[r * lda + lane] = (lane <= r) ? S[r][lane] : 0.0;
+}
+
+// ---- leaf: X[:, 0:w] <- X[:, 0:w] T^-T for a (w <= 32) lower-triangular block T --------------
+// 128 rows per CTA, one thread per row, row in registers, T broadcast from shared memory.
+__global__ void __launch_bounds__(128)
+trsm_leaf_kernel(const double* __restrict__ T, int64_t ldt, int w, double* __restrict__ X, int64_t ldx,
+                 int64_t nrows) {
+  __shared__ double Ts[NB][NB + 1];
+  __shared__ double Xs[128][NB + 1];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * NB; e += 128) {
+    int r = e / NB, c = e % NB;
+    Ts[r][c] = (r < w && c < w) ? T[r * ldt + c] : (r == c ? 1.0 : 0.0);
+  }
+  for (int64_t r0 = (int64_t)blockIdx.x * 128; r0 < nrows; r0 += (int64_t)gridDim.x * 128) {
+    __syncthreads();
+    for (int e = tid; e < 128 * NB; e += 128) {
+      int r = e / NB, c = e % NB;
+      Xs[r][c] = (r0 + r < nrows && c < w) ? X[(r0 + r) * ldx + c] : 0.0;
+    }
+    __syncthreads();
+    double x[NB];
+#pragma unroll
+    for (int c = 0; c < NB; c++) x[c] = Xs[tid][c];
+#pragma unroll
+    for (int c = 0; c < NB; c++) {
+      double s = x[c];
+#pragma unroll
+      for (int k = 0; k < c; k++) s = fma(-x[k], Ts[c][k], s);
+      x[c] = s / Ts[c][c];
+    }
+#pragma unroll
+    for (int c = 0; c < NB; c++) Xs[tid][c] = x[c];
+    __syncthreads();
+    for (int e = tid; e < 128 * NB; e += 128) {
+      int r = e / NB, c = e % NB;
+      if (r0 + r < nrows && c < w) X[(r0 + r) * ldx + c] = Xs[r][c];
+    }
+  }
+}
+
+int trsm_rec(mb_ctx* ctx, const double* Lp, int64_t ldl, int64_t c0, int64_t w, double* X, int64_t ldx,
+             int64_t nrows) {
+  if (w <= 0) return 0;
+  if (w <= NB) {
+    int grid = (int)min(ceil_div64(nrows, 128), (int64_t)ctx->n_sm * 8);
+    MB_LAUNCH(ctx, trsm_leaf_kernel, grid, 128, 0, Lp + c0 * ldl + c0, ldl, (int)w, X + c0, ldx, nrows);
+    return 0;
+  }
+  int64_t w1 = ((w / 2 + NB - 1) / NB) * NB;
+  MB_TRY(trsm_rec(ctx, Lp, ldl, c0, w1, X, ldx, nrows));
+  // X[:, c0+w1 : c0+w] -= X[:, c0 : c0+w1] . Lp[c0+w1 : c0+w, c0 : c0+w1]^T
+  MB_TRY(mb_gemm_raw(ctx, false, false, nrows, w - w1, w1, -1.0, X + c0, ldx, Lp + (c0 + w1) * ldl + c0, ldl,
+                     1.0, X + c0 + w1, ldx, false));
+  return trsm_rec(ctx, Lp, ldl, c0 + w1, w - w1, X, ldx, nrows);
+}
+
+int potrf_rec(mb_ctx* ctx, double* A, int64_t lda, int64_t off, int64_t n, int* info) {
+  if (n <= 0) return 0;
+  double* D = A + off * lda + off;
+  if (n <= NB) {
+    MB_LAUNCH(ctx, potrf_leaf_kernel, 1, 32, 0, D, lda, (int)n, off, info);
+    return 0;
+  }
+  int64_t n1 = ((n / 2 + NB - 1) / NB) * NB, n2 = n - n1;
+  MB_TRY(potrf_rec(ctx, A, lda, off, n1, info));
+  double* A21 = A + (off + n1) * lda + off;
+  // A21 <- A21 L11^-T
+  MB_TRY(trsm_rec(ctx, D, lda, 0, n1, A21, lda, n2));
+  // A22 <- A22 - A21 A21^T   (lower tiles only)
+  double* A22 = A + (off + n1) * lda + off + n1;
+  MB_TRY(mb_gemm_raw(ctx, false, false, n2, n2, n1, -1.0, A21, lda, A21, lda, 1.0, A22, lda, true));
+  return potrf_rec(ctx, A, lda, off + n1, n2, info);
+}
+
+__global__ void zero_upper_kernel(double* a, int64_t n, int64_t lda) {
+  int64_t i = blockIdx.y, j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n && j < n && j > i) a[i * lda + j] = 0.0;
+}
+
+// ---- vector triangular solves: one CTA per right-hand side ---------------------------------
+// forward:  L x = b     backward: L^T x = b.   x lives in shared memory (m doubles).
+__global__ void __launch_bounds__(1024)
+trsv_kernel(const double* __restrict__ L, int64_t ldl, int m, double* __restrict__ B, int nrhs, int trans) {
+  extern __shared__ double xs[];
+  __shared__ double T[NB][NB + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int col = blockIdx.x;
+  for (int i = tid; i < m; i += blockDim.x) xs[i] = B[(int64_t)i * nrhs + col];
+  __syncthreads();
+  const int nblk = (m + NB - 1) / NB;
+  for (int bb = 0; bb < nblk; bb++) {
+    const int b = trans ? nblk - 1 - bb : bb;
+    const int j0 = b * NB, w = min(NB, m - j0);
+    // stage the diagonal block
+    for (int e = tid; e < NB * NB; e += blockDim.x) {
+      int r = e / NB, c = e % NB;
+      T[r][c] = (r < w && c < w) ? L[(int64_t)(j0 + r) * ldl + j0 + c] : (r == c ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double xi = (lane < w) ? xs[j0 + lane] : 0.0;
+      if (!trans) {
+        for (int j = 0; j < w; j++) {
+          double v = __shfl_sync(0xffffffffu, xi, j) / T[j][j];
+          if (lane == j) xi = v;
+          if (lane > j) xi = fma(-T[lane][j], v, xi);
+        }
+      } else {
+        for (int j = w - 1; j >= 0; j--) {
+          double v = __shfl_sync(0xffffffffu, xi, j) / T[j][j];
+          if (lane == j) xi = v;
+          if (lane < j) xi = fma(-T[j][lane], v, xi);
+        }
+      }
+      if (lane < w) xs[j0 + lane] = xi;
+    }
+    __syncthreads();
+    if (!trans) {
+      // rows below the block: xs[i] -= sum_jj L[i][j0+jj] xs[j0+jj]
+      const double xj = (lane < w) ? xs[j0 + lane] : 0.0;
+      for (int i = j0 + NB + warp; i < m; i += nwarps) {
+        double v = (lane < w) ? L[(int64_t)i * ldl + j0 + lane] * xj : 0.0;
+        v = warp_sum(v);
+        if (lane == 0) xs[i] -= v;
+      }
+    } else {
+      // entries before the block: xs[i] -= sum_jj L[j0+jj][i] xs[j0+jj]
+      for (int i = tid; i < j0; i += blockDim.x) {
+        double s = 0.0;
+        for (int jj = 0; jj < w; jj++) s = fma(L[(int64_t)(j0 + jj) * ldl + i], xs[j0 + jj], s);
+        xs[i] -= s;
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < m; i += blockDim.x) B[(int64_t)i * nrhs + col] = xs[i];
+}
+
+}  // namespace
+
+int mb_trsm_right_lt_raw(mb_ctx* ctx, const double* Lp, int64_t ldl, int64_t m, double* X, int64_t ldx,
+                         int64_t nrows) {
+  if (nrows <= 0 || m <= 0) return 0;
+  return trsm_rec(ctx, Lp, ldl, 0, m, X, ldx, nrows);
+}
+
+int mb_potrf_raw(mb_ctx* ctx, double* A, int64_t n, int64_t lda, int* info_dev) {
+  MB_TRY(potrf_rec(ctx, A, lda, 0, n, info_dev));
+  if (n > 0) {
+    dim3 grid((unsigned)ceil_div64(n, 256), (unsigned)n);
+    MB_CHECK(n < 65536 * 1, "mb_potrf: n=%lld too large for the zero-upper grid", (long long)n);
+    MB_LAUNCH(ctx, zero_upper_kernel, grid, 256, 0, A, n, lda);
+  }
+  return 0;
+}
+
+extern "C" int mb_potrf(mb_ctx* ctx, mb_mat* a) {
+  MB_CHECK(ctx && a, "mb_potrf: null argument");
+  MB_CHECK(a->rows == a->cols, "mb_potrf: matrix is %lld x %lld, not square", (long long)a->rows,
+           (long long)a->cols);
+  MB_CUDA(cudaSetDevice(ctx->device));
+  if (a->rows == 0) return 0;
+  double* scratch;
+  MB_TRY(mb_scratch(ctx, 256, &scratch));
+  int* info_dev = reinterpret_cast<int*>(scratch);
+  MB_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), ctx->stream));
+  MB_TRY(mb_potrf_raw(ctx, a->p, a->rows, a->cols, info_dev));
+  int info = 0;
+  MB_CUDA(cudaMemcpyAsync(&info, info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  MB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return info;  // > 0: first non-positive pivot (1-based)
+}
+
+extern "C" int mb_trsm_right_lt(mb_ctx* ctx, const mb_mat* Lp, mb_mat* X) {
+  MB_CHECK(ctx && Lp && X, "mb_trsm_right_lt: null argument");
+  MB_CHECK(Lp->rows == Lp->cols && X->cols == Lp->rows,
+           "mb_trsm_right_lt: Lp is %lld x %lld, X is %lld x %lld", (long long)Lp->rows,
+           (long long)Lp->cols, (long long)X->rows, (long long)X->cols);
+  MB_CUDA(cudaSetDevice(ctx->device));
+  return mb_trsm_right_lt_raw(ctx, Lp->p, Lp->cols, Lp->rows, X->p, X->cols, X->rows);
+}
+
+extern "C" int mb_tri_solve(mb_ctx* ctx, const mb_mat* Lp, int trans, mb_mat* B) {
+  MB_CHECK(ctx && Lp && B, "mb_tri_solve: null argument");
+  MB_CHECK(Lp->rows == Lp->cols && B->rows == Lp->rows, "mb_tri_solve: Lp is %lld x %lld, B has %lld rows",
+           (long long)Lp->rows, (long long)Lp->cols, (long long)B->rows);
+  MB_CUDA(cudaSetDevice(ctx->device));
+  const int64_t m = Lp->rows, nrhs = B->cols;
+  if (m == 0 || nrhs == 0) return 0;
+  const size_t smem = (size_t)m * sizeof(double);
+  if (nrhs <= 64 && smem <= 200 * 1024) {
+    static bool configured = false;
+    if (!configured) {
+      MB_CUDA(cudaFuncSetAttribute(trsv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    MB_LAUNCH(ctx, trsv_kernel, (int)nrhs, 1024, smem, Lp->p, Lp->cols, (int)m, B->p, (int)nrhs, trans);
+    return 0;
+  }
+  // wide right-hand sides: (Lp^-1 B)^T = B^T Lp^-T  -> transpose, right-side solve, transpose back
+  MB_CHECK(!trans, "mb_tri_solve: transposed solve supports at most 64 right-hand sides and m <= 25600");
+  double* scratch;
+  MB_TRY(mb_scratch(ctx, (size_t)m * nrhs * sizeof(double), &scratch));
+  mb_mat bt = {scratch, nrhs, m, ctx, false};
+  MB_TRY(mb_mat_transpose(ctx, B, &bt));
+  MB_TRY(mb_trsm_right_lt_raw(ctx, Lp->p, Lp->cols, m, bt.p, m, nrhs));
+  return mb_mat_transpose(ctx, &bt, B);
+}

@@ -1,0 +1,108 @@
+// Shared internals of libmellon_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/mellon_b200.h"
+
+struct mb_mat {
+  double* p;
+  int64_t rows, cols;
+  mb_ctx* ctx;
+  bool owns;
+};
+
+struct mb_ctx {
+  int device;
+  int n_sm;
+  cudaStream_t stream;       // compute stream (everything is ordered on it)
+  cudaStream_t copy_stream;  // H2D/D2H overlap for the streaming predictor
+  cudaEvent_t timer_ev[16][2];
+  cudaEvent_t ev_a, ev_b;
+  int64_t launches;
+  // scratch
+  double* scratch;           // reusable device scratch
+  size_t scratch_bytes;
+  double* pinned;            // reusable pinned host staging
+  size_t pinned_bytes;
+  double* flush_buf;
+  size_t flush_bytes;
+  // NCCL
+  void* comm;
+  int rank, world;
+  // options
+  int opt_gemm;      // 0 = DMMA tiles (default), 1 = DFMA register tiles
+  int opt_cov;       // 0 = default tile kernel
+  int opt_lossgrad;  // 0 = fused single pass, 1 = two-pass
+};
+
+void mb_set_error(const char* fmt, ...);
+
+#define MB_CUDA(call)                                                              \
+  do {                                                                             \
+    cudaError_t _e = (call);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      mb_set_error("%s:%d CUDA error: %s (%s)", __FILE__, __LINE__,                \
+                   cudaGetErrorString(_e), #call);                                 \
+      return -1;                                                                   \
+    }                                                                              \
+  } while (0)
+
+#define MB_CHECK(cond, ...)                                                        \
+  do {                                                                             \
+    if (!(cond)) {                                                                 \
+      mb_set_error(__VA_ARGS__);                                                   \
+      return -2;                                                                   \
+    }                                                                              \
+  } while (0)
+
+#define MB_TRY(call)                                                               \
+  do {                                                                             \
+    int _r = (call);                                                               \
+    if (_r != 0) return _r;                                                        \
+  } while (0)
+
+// Every kernel launch goes through this so the context can count them and catch
+// launch-configuration errors at the call site.
+#define MB_LAUNCH(ctx, kernel, grid, block, smem, ...)                             \
+  do {                                                                             \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);               \
+    (ctx)->launches++;                                                             \
+    MB_CUDA(cudaGetLastError());                                                   \
+  } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// scratch management (grows monotonically; contents undefined)
+int mb_scratch(mb_ctx* ctx, size_t bytes, double** out);
+int mb_pinned(mb_ctx* ctx, size_t bytes, double** out);
+
+// internal helpers implemented across translation units
+int mb_mat_view(mb_ctx* ctx, double* p, int64_t rows, int64_t cols, mb_mat* out);
+
+// GEMM on raw pointers with leading dimensions (row-major).
+//   a_kmajor=0: A element (i,k) at A[i*lda + k];  a_kmajor=1: at A[k*lda + i]
+//   b_kmajor=0: B element (j,k) at B[j*ldb + k];  b_kmajor=1: at B[k*ldb + j]
+//   C[i*ldc + j] = alpha * sum_k A(i,k) B(j,k) + beta * C[i*ldc + j]
+//   lower_only: skip output tiles strictly above the diagonal (SYRK-style).
+int mb_gemm_raw(mb_ctx* ctx, bool a_kmajor, bool b_kmajor, int64_t m, int64_t n, int64_t k,
+                double alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
+                double beta, double* C, int64_t ldc, bool lower_only);
+
+int mb_potrf_raw(mb_ctx* ctx, double* A, int64_t n, int64_t lda, int* info_dev_accum);
+int mb_trsm_right_lt_raw(mb_ctx* ctx, const double* Lp, int64_t ldl, int64_t m, double* X,
+                         int64_t ldx, int64_t nrows);
+int mb_allreduce_raw(mb_ctx* ctx, double* p, int64_t count);
+
+// warp / block reductions -------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}

@@ -1,0 +1,336 @@
+// FP64 GEMM on the tensor pipe (DMMA m8n8k4, the native f64 MMA shape on sm_100a) with a
+// 3-stage cp.async pipeline.  Used by K3 (TRSM updates), K4 (Gram / SYRK), K2 (Cholesky
+// trailing updates) and the Nystroem products.
+//
+//   C[i*ldc + j] = alpha * sum_k A(i,k) * B(j,k) + beta * C[i*ldc + j]
+//   A(i,k) = A[i*lda + k] (AK=false)  or  A[k*lda + i] (AK=true,  "k-major")
+//   B(j,k) = B[j*ldb + k] (BK=false)  or  B[k*ldb + j] (BK=true)
+//
+// CTA tile 128x128x16, 8 warps (2 x 4), warp tile 64x32 = 8x4 DMMA tiles.
+#include "mb_common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BKT = 16, STAGES = 3, NTHREADS = 256;
+constexpr int LD_ROWMAJ = BKT + 4;   // [tile_rows][BKT+4]   (stride 20: 4*m + k distinct mod 16)
+constexpr int LD_KMAJ = BM + 4;      // [BKT][tile_rows+4]   (stride 132: 4*k + m distinct mod 16)
+constexpr int TILE_DOUBLES = BM * LD_ROWMAJ;  // 2560 >= BKT * LD_KMAJ (2112)
+constexpr size_t SMEM_BYTES = (size_t)STAGES * 2 * TILE_DOUBLES * sizeof(double);
+
+__device__ __forceinline__ void cp_async16(double* smem, const double* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(double* smem, const double* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Load one operand tile (tile_rows = 128 "row" indices x BKT k indices) into shared memory.
+// KMAJ=false: source element (r, k) at src[(r0+r)*ld + k0+k]  -> dst[r*LD_ROWMAJ + k]
+// KMAJ=true : source element (r, k) at src[(k0+k)*ld + r0+r]  -> dst[k*LD_KMAJ + r]
+template <bool KMAJ>
+__device__ __forceinline__ void load_tile(double* dst, const double* __restrict__ src, int64_t ld,
+                                          int64_t r0, int64_t nr, int64_t k0, int64_t nk, bool vec_ok,
+                                          int tid) {
+  if (!KMAJ) {
+    if (vec_ok) {
+#pragma unroll
+      for (int it = 0; it < (BM * BKT / 2) / NTHREADS; it++) {
+        int e = tid + it * NTHREADS;
+        int r = e / (BKT / 2), c = (e % (BKT / 2)) * 2;
+        int64_t gr = r0 + r, gk = k0 + c;
+        int bytes = 0;
+        if (gr < nr) {
+          int64_t rem = nk - gk;
+          bytes = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+        }
+        const double* g = bytes ? src + gr * ld + gk : src;
+        cp_async16(dst + r * LD_ROWMAJ + c, g, bytes);
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < (BM * BKT) / NTHREADS; it++) {
+        int e = tid + it * NTHREADS;
+        int r = e / BKT, c = e % BKT;
+        int64_t gr = r0 + r, gk = k0 + c;
+        int bytes = (gr < nr && gk < nk) ? 8 : 0;
+        const double* g = bytes ? src + gr * ld + gk : src;
+        cp_async8(dst + r * LD_ROWMAJ + c, g, bytes);
+      }
+    }
+  } else {
+    if (vec_ok) {
+#pragma unroll
+      for (int it = 0; it < (BM * BKT / 2) / NTHREADS; it++) {
+        int e = tid + it * NTHREADS;
+        int k = e / (BM / 2), c = (e % (BM / 2)) * 2;
+        int64_t gk = k0 + k, gr = r0 + c;
+        int bytes = 0;
+        if (gk < nk) {
+          int64_t rem = nr - gr;
+          bytes = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+        }
+        const double* g = bytes ? src + gk * ld + gr : src;
+        cp_async16(dst + k * LD_KMAJ + c, g, bytes);
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < (BM * BKT) / NTHREADS; it++) {
+        int e = tid + it * NTHREADS;
+        int k = e / BM, c = e % BM;
+        int64_t gk = k0 + k, gr = r0 + c;
+        int bytes = (gk < nk && gr < nr) ? 8 : 0;
+        const double* g = bytes ? src + gk * ld + gr : src;
+        cp_async8(dst + k * LD_KMAJ + c, g, bytes);
+      }
+    }
+  }
+}
+
+template <bool AK, bool BK>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_dmma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __restrict__ A, int64_t lda,
+                 const double* __restrict__ B, int64_t ldb, double beta, double* __restrict__ C,
+                 int64_t ldc, int lower_only, int64_t tiles_n, int64_t n_tiles, int a_vec, int b_vec) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
+  const int lr = lane >> 2, lk = lane & 3;
+  const int64_t nkt = (k + BKT - 1) / BKT;
+
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    int64_t bi, bj;
+    if (lower_only) {
+      // t enumerates (bi, bj) with bj <= bi, row by row
+      bi = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+      while ((bi + 1) * (bi + 2) / 2 <= t) bi++;
+      while (bi * (bi + 1) / 2 > t) bi--;
+      bj = t - bi * (bi + 1) / 2;
+    } else {
+      bi = t / tiles_n;
+      bj = t % tiles_n;
+    }
+    const int64_t m0 = bi * BM, n0 = bj * BN;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // prologue
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+      if (s < nkt) {
+        double* sa = smem + (size_t)s * 2 * TILE_DOUBLES;
+        double* sb = sa + TILE_DOUBLES;
+        load_tile<AK>(sa, A, lda, m0, m, (int64_t)s * BKT, k, a_vec, tid);
+        load_tile<BK>(sb, B, ldb, n0, n, (int64_t)s * BKT, k, b_vec, tid);
+      }
+      cp_async_commit();
+    }
+
+    for (int64_t kt = 0; kt < nkt; kt++) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      {
+        int64_t nt = kt + STAGES - 1;
+        if (nt < nkt) {
+          int s = (int)(nt % STAGES);
+          double* sa = smem + (size_t)s * 2 * TILE_DOUBLES;
+          double* sb = sa + TILE_DOUBLES;
+          load_tile<AK>(sa, A, lda, m0, m, nt * BKT, k, a_vec, tid);
+          load_tile<BK>(sb, B, ldb, n0, n, nt * BKT, k, b_vec, tid);
+        }
+        cp_async_commit();
+      }
+      const double* sa = smem + (size_t)(kt % STAGES) * 2 * TILE_DOUBLES;
+      const double* sb = sa + TILE_DOUBLES;
+#pragma unroll
+      for (int ks = 0; ks < BKT / 4; ks++) {
+        double af[8], bf[4];
+        const int kk = ks * 4 + lk;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          int r = wm0 + i * 8 + lr;
+          af[i] = AK ? sa[kk * LD_KMAJ + r] : sa[r * LD_ROWMAJ + kk];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          int c = wn0 + j * 8 + lr;
+          bf[j] = BK ? sb[kk * LD_KMAJ + c] : sb[c * LD_ROWMAJ + kk];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // epilogue
+    const bool c_vec = ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      int64_t row = m0 + wm0 + i * 8 + lr;
+      if (row >= m) continue;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        int64_t col = n0 + wn0 + j * 8 + lk * 2;
+        if (col >= n) continue;
+        double* cp = C + row * ldc + col;
+        double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
+        if (col + 1 < n) {
+          if (c_vec) {
+            if (beta != 0.0) {
+              double2 old = *reinterpret_cast<double2*>(cp);
+              v0 += beta * old.x;
+              v1 += beta * old.y;
+            }
+            *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
+          } else {
+            if (beta != 0.0) {
+              v0 += beta * cp[0];
+              v1 += beta * cp[1];
+            }
+            cp[0] = v0;
+            cp[1] = v1;
+          }
+        } else {
+          if (beta != 0.0) v0 += beta * cp[0];
+          cp[0] = v0;
+        }
+      }
+    }
+  }
+}
+
+// ---- DFMA register-tiled reference variant (opt_gemm = 1): A/B measurement only -----------
+// 64x64 tile, 256 threads, 4x4 micro-tile, no pipelining: simple and obviously correct.
+template <bool AK, bool BK>
+__global__ void __launch_bounds__(256)
+gemm_dfma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __restrict__ A, int64_t lda,
+                 const double* __restrict__ B, int64_t ldb, double beta, double* __restrict__ C,
+                 int64_t ldc, int lower_only, int64_t tiles_n, int64_t n_tiles) {
+  __shared__ double sa[16][64 + 1], sb[16][64 + 1];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    int64_t bi = t / tiles_n, bj = t % tiles_n;
+    if (lower_only && bj > bi) continue;
+    const int64_t m0 = bi * 64, n0 = bj * 64;
+    double acc[4][4] = {};
+    for (int64_t k0 = 0; k0 < k; k0 += 16) {
+      for (int e = tid; e < 64 * 16; e += 256) {
+        int r, kk;
+        if (AK) { kk = e / 64; r = e % 64; } else { r = e / 16; kk = e % 16; }
+        int64_t gr = m0 + r, gk = k0 + kk;
+        sa[kk][r] = (gr < m && gk < k) ? (AK ? A[gk * lda + gr] : A[gr * lda + gk]) : 0.0;
+        if (BK) { kk = e / 64; r = e % 64; } else { r = e / 16; kk = e % 16; }
+        gr = n0 + r; gk = k0 + kk;
+        sb[kk][r] = (gr < n && gk < k) ? (BK ? B[gk * ldb + gr] : B[gr * ldb + gk]) : 0.0;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < 16; kk++) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = sa[kk][ty + 16 * i];
+#pragma unroll
+        for (int j = 0; j < 4; j++) b[j] = sb[kk][tx + 16 * j];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int64_t row = m0 + ty + 16 * i;
+      if (row >= m) continue;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        int64_t col = n0 + tx + 16 * j;
+        if (col >= n) continue;
+        double v = alpha * acc[i][j];
+        if (beta != 0.0) v += beta * C[row * ldc + col];
+        C[row * ldc + col] = v;
+      }
+    }
+  }
+}
+
+template <bool AK, bool BK>
+int launch_gemm(mb_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only) {
+  if (ctx->opt_gemm == 1) {
+    int64_t tm = ceil_div64(m, 64), tn = ceil_div64(n, 64), nt = tm * tn;
+    int grid = (int)min(nt, (int64_t)ctx->n_sm * 8);
+    MB_LAUNCH(ctx, (gemm_dfma_kernel<AK, BK>), grid, 256, 0, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc,
+              lower_only ? 1 : 0, tn, nt);
+    return 0;
+  }
+  static bool configured = false;
+  if (!configured) {
+    MB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    MB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    MB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    MB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    configured = true;
+  }
+  int64_t tm = ceil_div64(m, BM), tn = ceil_div64(n, BN);
+  int64_t nt = lower_only ? tm * (tm + 1) / 2 : tm * tn;
+  if (lower_only) MB_CHECK(m == n, "gemm lower_only needs a square output");
+  int grid = (int)min(nt, (int64_t)ctx->n_sm);
+  int a_vec = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  int b_vec = ((ldb & 1) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  MB_LAUNCH(ctx, (gemm_dmma_kernel<AK, BK>), grid, NTHREADS, SMEM_BYTES, m, n, k, alpha, A, lda, B, ldb, beta,
+            C, ldc, lower_only ? 1 : 0, tn, nt, a_vec, b_vec);
+  return 0;
+}
+
+}  // namespace
+
+int mb_gemm_raw(mb_ctx* ctx, bool a_kmajor, bool b_kmajor, int64_t m, int64_t n, int64_t k, double alpha,
+                const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
+                int64_t ldc, bool lower_only) {
+  if (m <= 0 || n <= 0) return 0;
+  MB_CUDA(cudaSetDevice(ctx->device));
+  if (a_kmajor) {
+    if (b_kmajor) return launch_gemm<true, true>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only);
+    return launch_gemm<true, false>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only);
+  }
+  if (b_kmajor) return launch_gemm<false, true>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only);
+  return launch_gemm<false, false>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only);
+}
+
+// C = alpha op(A) op(B) + beta C with row-major matrices.
+//   op(A) (m x k): trans_a=0 -> A is m x k (A(i,k)=A[i*lda+k], not k-major); trans_a=1 -> A is k x m (k-major)
+//   op(B) (k x n): trans_b=0 -> B is k x n (B(j,k)=B[k*ldb+j], k-major);     trans_b=1 -> B is n x k (not k-major)
+extern "C" int mb_gemm(mb_ctx* ctx, int trans_a, int trans_b, double alpha, const mb_mat* A, const mb_mat* B,
+                       double beta, mb_mat* C) {
+  MB_CHECK(ctx && A && B && C, "mb_gemm: null argument");
+  int64_t m = trans_a ? A->cols : A->rows, ka = trans_a ? A->rows : A->cols;
+  int64_t n = trans_b ? B->rows : B->cols, kb = trans_b ? B->cols : B->rows;
+  MB_CHECK(ka == kb, "mb_gemm: inner dimensions differ (%lld vs %lld)", (long long)ka, (long long)kb);
+  MB_CHECK(C->rows == m && C->cols == n, "mb_gemm: output is %lld x %lld, expected %lld x %lld",
+           (long long)C->rows, (long long)C->cols, (long long)m, (long long)n);
+  if (ka == 0) {
+    if (beta == 0.0) return mb_mat_fill(ctx, C, 0.0);
+  }
+  return mb_gemm_raw(ctx, trans_a != 0, trans_b == 0, m, n, ka, alpha, A->p, A->cols, B->p, B->cols, beta, C->p,
+                     C->cols, false);
+}

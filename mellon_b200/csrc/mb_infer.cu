@@ -1,0 +1,413 @@
+// K5 / K6 and the O(N r) passes over L: MAP objective value + gradient, transform,
+// Hessian diagonal, L^T t.  HBM-bound streaming kernels; every reduction is a fixed-order
+// tree so results are bit-reproducible run to run and identical on every rank after the
+// all-reduce.
+#include "mb_common.cuh"
+
+namespace {
+
+constexpr int ROW_THREADS = 256;   // 8 warps per CTA, one row per warp at a time
+enum { MODE_TRANSFORM = 0, MODE_GRAD = 1, MODE_HESS = 2 };
+
+// f_i = L[i,:] . z + mu ; per mode:
+//   TRANSFORM: out_f[i] = f_i
+//   GRAD:      wv[i] = exp(f_i + V_i) - 1 ; partial[block] = sum (f_i - A_i)
+//   HESS:      wv[i] = exp(f_i + V_i)
+template <int MODE>
+__global__ void __launch_bounds__(ROW_THREADS)
+rowdot_kernel(const double* __restrict__ L, int64_t n, int r, const double* __restrict__ z, double mu,
+              const double* __restrict__ V, double* __restrict__ out, double* __restrict__ partial) {
+  extern __shared__ double zs[];
+  __shared__ double red[ROW_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int c = tid; c < r; c += ROW_THREADS) zs[c] = z[c];
+  __syncthreads();
+  const int64_t warps_total = (int64_t)gridDim.x * (ROW_THREADS / 32);
+  const bool vec = ((r & 1) == 0) && ((reinterpret_cast<uintptr_t>(L) & 15) == 0);
+  double local = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * (ROW_THREADS / 32) + warp; i < n; i += warps_total) {
+    const double* row = L + i * r;
+    double s0 = 0.0, s1 = 0.0;
+    if (vec) {
+      const double2* row2 = reinterpret_cast<const double2*>(row);
+      const int r2 = r >> 1;
+      int c = lane;
+      for (; c + 96 < r2; c += 128) {
+        double2 a = row2[c], b = row2[c + 32], d = row2[c + 64], e = row2[c + 96];
+        s0 = fma(a.x, zs[2 * c], s0);            s1 = fma(a.y, zs[2 * c + 1], s1);
+        s0 = fma(b.x, zs[2 * (c + 32)], s0);     s1 = fma(b.y, zs[2 * (c + 32) + 1], s1);
+        s0 = fma(d.x, zs[2 * (c + 64)], s0);     s1 = fma(d.y, zs[2 * (c + 64) + 1], s1);
+        s0 = fma(e.x, zs[2 * (c + 96)], s0);     s1 = fma(e.y, zs[2 * (c + 96) + 1], s1);
+      }
+      for (; c < r2; c += 32) {
+        double2 a = row2[c];
+        s0 = fma(a.x, zs[2 * c], s0);
+        s1 = fma(a.y, zs[2 * c + 1], s1);
+      }
+    } else {
+      for (int c = lane; c < r; c += 32) s0 = fma(row[c], zs[c], s0);
+    }
+    double f = warp_sum(s0 + s1) + mu;
+    if (lane == 0) {
+      if (MODE == MODE_TRANSFORM) {
+        out[i] = f;
+      } else {
+        double A = exp(f + V[i]);
+        out[i] = (MODE == MODE_GRAD) ? (A - 1.0) : A;
+        if (MODE == MODE_GRAD) local += f - A;
+      }
+    }
+  }
+  if (MODE == MODE_GRAD) {
+    if (lane == 0) red[warp] = local;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int w = 0; w < ROW_THREADS / 32; w++) s += red[w];
+      partial[blockIdx.x] = s;
+    }
+  }
+}
+
+// partial[chunk][c] = sum_{i in chunk} wv[i] * (SQ ? L[i,c]^2 : L[i,c])
+template <bool SQ>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const double* __restrict__ L, int64_t n, int r, const double* __restrict__ wv,
+              int64_t rows_per_chunk, double* __restrict__ partial) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 2;
+  const int64_t i0 = (int64_t)blockIdx.y * rows_per_chunk;
+  const int64_t i1 = min(n, i0 + rows_per_chunk);
+  if (c >= r) return;
+  const bool pair = (c + 1 < r);
+  const bool vec = pair && ((r & 1) == 0) && ((reinterpret_cast<uintptr_t>(L) & 15) == 0);
+  double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+  int64_t i = i0;
+  if (vec) {
+    for (; i + 3 < i1; i += 4) {
+      double2 v0 = *reinterpret_cast<const double2*>(L + i * r + c);
+      double2 v1 = *reinterpret_cast<const double2*>(L + (i + 1) * r + c);
+      double2 v2 = *reinterpret_cast<const double2*>(L + (i + 2) * r + c);
+      double2 v3 = *reinterpret_cast<const double2*>(L + (i + 3) * r + c);
+      double w0 = wv[i], w1 = wv[i + 1], w2 = wv[i + 2], w3 = wv[i + 3];
+      if (SQ) {
+        v0.x *= v0.x; v0.y *= v0.y; v1.x *= v1.x; v1.y *= v1.y;
+        v2.x *= v2.x; v2.y *= v2.y; v3.x *= v3.x; v3.y *= v3.y;
+      }
+      a0 = fma(w0, v0.x, a0); a1 = fma(w0, v0.y, a1);
+      b0 = fma(w1, v1.x, b0); b1 = fma(w1, v1.y, b1);
+      a0 = fma(w2, v2.x, a0); a1 = fma(w2, v2.y, a1);
+      b0 = fma(w3, v3.x, b0); b1 = fma(w3, v3.y, b1);
+    }
+  }
+  for (; i < i1; i++) {
+    double w = wv[i];
+    double x = L[i * r + c], y = pair ? L[i * r + c + 1] : 0.0;
+    if (SQ) { x *= x; y *= y; }
+    a0 = fma(w, x, a0);
+    a1 = fma(w, y, a1);
+  }
+  double* p = partial + (int64_t)blockIdx.y * r;
+  p[c] = a0 + b0;
+  if (pair) p[c + 1] = a1 + b1;
+}
+
+// out[c] = sum_chunk partial[chunk][c]  (fixed order) ; out[r] = sum_b lpartial[b] when n_lp > 0
+__global__ void reduce_chunks_kernel(const double* __restrict__ partial, int n_chunks, int r,
+                                     const double* __restrict__ lpartial, int n_lp, double* __restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < r) {
+    double s = 0.0;
+    for (int k = 0; k < n_chunks; k++) s += partial[(int64_t)k * r + c];
+    out[c] = s;
+  } else if (c == r && n_lp > 0) {
+    double s = 0.0;
+    for (int k = 0; k < n_lp; k++) s += lpartial[k];
+    out[r] = s;
+  }
+}
+
+// ---- fused single pass (default): L is read from HBM exactly once per evaluation -----------
+// CTA = 512 threads; thread t owns columns {2t, 2t+1} + 1024 q (q < CP column pairs) and keeps
+// their gradient accumulators in registers.  Rows are processed RG at a time: the CTA loads
+// the RG x r slab straight into registers (coalesced 16-byte loads), block-reduces the RG row
+// dots, evaluates A = exp(f + V) and accumulates (A-1) * L from the same registers.
+template <int CP, int RG, bool SQ>
+__global__ void __launch_bounds__(512, 1)
+fused_rows_kernel(const double* __restrict__ L, int64_t n, int r, const double* __restrict__ z, double mu,
+                  const double* __restrict__ V, int64_t rows_per_cta, double* __restrict__ partial,
+                  double* __restrict__ lpartial) {
+  constexpr int T = 512, NW = T / 32;
+  __shared__ double red[2][RG][NW];
+  __shared__ double fsh[2][RG];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t i0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t i1 = min(n, i0 + rows_per_cta);
+
+  double2 zr[CP], g[CP];
+#pragma unroll
+  for (int q = 0; q < CP; q++) {
+    int c = 2 * tid + 2 * T * q;
+    zr[q].x = (c < r) ? z[c] : 0.0;
+    zr[q].y = (c + 1 < r) ? z[c + 1] : 0.0;
+    g[q] = make_double2(0.0, 0.0);
+  }
+  double lsum = 0.0;
+  int buf = 0;
+  for (int64_t ib = i0; ib < i1; ib += RG, buf ^= 1) {
+    double2 v[RG][CP];
+#pragma unroll
+    for (int rr = 0; rr < RG; rr++) {
+      const int64_t i = ib + rr;
+#pragma unroll
+      for (int q = 0; q < CP; q++) {
+        int c = 2 * tid + 2 * T * q;
+        v[rr][q] = (i < i1 && c < r) ? *reinterpret_cast<const double2*>(L + i * r + c)
+                                     : make_double2(0.0, 0.0);
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < RG; rr++) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < CP; q++) s = fma(v[rr][q].x, zr[q].x, fma(v[rr][q].y, zr[q].y, s));
+      s = warp_sum(s);
+      if (lane == 0) red[buf][rr][warp] = s;
+    }
+    __syncthreads();
+    if (tid < RG) {
+      double f = mu;
+#pragma unroll
+      for (int w = 0; w < NW; w++) f += red[buf][tid][w];
+      const int64_t i = ib + tid;
+      double wgt = 0.0;
+      if (i < i1) {
+        double A = exp(f + V[i]);
+        wgt = SQ ? A : (A - 1.0);
+        if (!SQ) lsum += f - A;
+      }
+      fsh[buf][tid] = wgt;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < RG; rr++) {
+      const double wgt = fsh[buf][rr];
+#pragma unroll
+      for (int q = 0; q < CP; q++) {
+        double x = v[rr][q].x, y = v[rr][q].y;
+        if (SQ) { x *= x; y *= y; }
+        g[q].x = fma(wgt, x, g[q].x);
+        g[q].y = fma(wgt, y, g[q].y);
+      }
+    }
+  }
+  double* p = partial + (int64_t)blockIdx.x * r;
+#pragma unroll
+  for (int q = 0; q < CP; q++) {
+    int c = 2 * tid + 2 * T * q;
+    if (c < r) p[c] = g[q].x;
+    if (c + 1 < r) p[c + 1] = g[q].y;
+  }
+  if (!SQ) {
+    // lsum lives in threads 0..RG-1 of warp 0
+    if (warp == 0) {
+      double s = warp_sum(tid < RG ? lsum : 0.0);
+      if (lane == 0) lpartial[blockIdx.x] = s;
+    }
+  }
+}
+
+struct PassBuffers {
+  double* zdev;      // r
+  double* wv;        // n
+  double* partial;   // chunks * r
+  double* lpartial;  // up to 4096
+  double* out;       // r + 1
+};
+
+int carve(mb_ctx* ctx, int64_t n, int r, int64_t chunks, PassBuffers* pb) {
+  size_t need = ((size_t)r + (size_t)n + (size_t)chunks * r + 4096 + (size_t)r + 8) * sizeof(double);
+  double* s;
+  MB_TRY(mb_scratch(ctx, need, &s));
+  pb->zdev = s;
+  pb->wv = pb->zdev + r + (r & 1);
+  pb->partial = pb->wv + n + (n & 1);
+  pb->lpartial = pb->partial + chunks * r;
+  pb->out = pb->lpartial + 4096;
+  return 0;
+}
+
+template <int MODE>
+int launch_rowdot(mb_ctx* ctx, const mb_mat* L, const double* zdev, double mu, const double* V, double* out,
+                  double* partial, int* nblocks) {
+  int grid = (int)min((int64_t)ctx->n_sm * 4, ceil_div64(L->rows, ROW_THREADS / 32));
+  grid = max(grid, 1);
+  size_t smem = (size_t)L->cols * sizeof(double);
+  MB_CHECK(smem <= 160 * 1024, "rank %lld too large for the row-dot kernel (max 20480)", (long long)L->cols);
+  static bool configured[3] = {false, false, false};
+  if (!configured[MODE]) {
+    MB_CUDA(cudaFuncSetAttribute(rowdot_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    configured[MODE] = true;
+  }
+  MB_LAUNCH(ctx, rowdot_kernel<MODE>, grid, ROW_THREADS, smem, L->p, L->rows, (int)L->cols, zdev, mu, V, out,
+            partial);
+  if (nblocks) *nblocks = grid;
+  return 0;
+}
+
+// two-pass route: (A-1 | A | t) weights in wv, then column sums
+int colsum(mb_ctx* ctx, const mb_mat* L, const double* wv, bool sq, PassBuffers* pb, int64_t chunks,
+           const double* lpartial, int n_lp) {
+  const int r = (int)L->cols;
+  int64_t rows_per_chunk = ceil_div64(L->rows, chunks);
+  dim3 grid((unsigned)ceil_div64(r, 512), (unsigned)chunks);
+  if (sq) MB_LAUNCH(ctx, colsum_kernel<true>, grid, 256, 0, L->p, L->rows, r, wv, rows_per_chunk, pb->partial);
+  else MB_LAUNCH(ctx, colsum_kernel<false>, grid, 256, 0, L->p, L->rows, r, wv, rows_per_chunk, pb->partial);
+  MB_LAUNCH(ctx, reduce_chunks_kernel, (int)ceil_div64(r + 1, 256), 256, 0, pb->partial, (int)chunks, r, lpartial,
+            n_lp, pb->out);
+  return 0;
+}
+
+int64_t pick_chunks(mb_ctx* ctx, int64_t n, int r) {
+  int64_t col_blocks = ceil_div64(r, 512);
+  int64_t chunks = ceil_div64((int64_t)ctx->n_sm * 4, col_blocks);
+  chunks = min(chunks, ceil_div64(n, 64));
+  return std::max<int64_t>(chunks, 1);
+}
+
+template <bool SQ>
+int launch_fused(mb_ctx* ctx, const mb_mat* L, const double* zdev, double mu, const double* V, PassBuffers* pb,
+                 int64_t n_cta, bool* done) {
+  const int r = (int)L->cols;
+  const int64_t n = L->rows;
+  *done = false;
+  if ((r & 1) || (reinterpret_cast<uintptr_t>(L->p) & 15)) return 0;
+  const int cp = (int)ceil_div64(r, 1024);
+  int64_t rows_per_cta = ceil_div64(n, n_cta);
+#define MB_FUSED(CPV, RGV)                                                                                \
+  {                                                                                                       \
+    rows_per_cta = ceil_div64(rows_per_cta, RGV) * RGV;                                                   \
+    int grid = (int)ceil_div64(n, rows_per_cta);                                                          \
+    MB_LAUNCH(ctx, (fused_rows_kernel<CPV, RGV, SQ>), grid, 512, 0, L->p, n, r, zdev, mu, V, rows_per_cta, \
+              pb->partial, pb->lpartial);                                                                 \
+    MB_LAUNCH(ctx, reduce_chunks_kernel, (int)ceil_div64(r + 1, 256), 256, 0, pb->partial, grid, r,       \
+              pb->lpartial, SQ ? 0 : grid, pb->out);                                                      \
+    *done = true;                                                                                         \
+  }
+  if (cp == 1) MB_FUSED(1, 8)
+  else if (cp == 2) MB_FUSED(2, 8)
+  else if (cp <= 3) MB_FUSED(3, 4)
+  else if (cp <= 4) MB_FUSED(4, 4)
+  else if (cp <= 5) MB_FUSED(5, 4)
+  else if (cp <= 6) MB_FUSED(6, 2)
+  else if (cp <= 8) MB_FUSED(8, 2)
+#undef MB_FUSED
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int mb_transform(mb_ctx* ctx, const mb_mat* L, const double* z_host, double mu, double* f_host) {
+  MB_CHECK(ctx && L && z_host && (f_host || L->rows == 0), "mb_transform: null argument");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = L->rows;
+  const int r = (int)L->cols;
+  if (n == 0) return 0;
+  PassBuffers pb;
+  MB_TRY(carve(ctx, n, r, 1, &pb));
+  MB_CUDA(cudaMemcpyAsync(pb.zdev, z_host, (size_t)r * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  MB_TRY(launch_rowdot<MODE_TRANSFORM>(ctx, L, pb.zdev, mu, nullptr, pb.wv, nullptr, nullptr));
+  MB_CUDA(cudaMemcpyAsync(f_host, pb.wv, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  MB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int mb_loss_grad(mb_ctx* ctx, const mb_mat* L, const mb_mat* V, double sum_vdr, double mu, double k,
+                            const double* z_host, double* loss, double* grad_host) {
+  MB_CHECK(ctx && L && V && z_host && loss && grad_host, "mb_loss_grad: null argument");
+  MB_CHECK(V->rows * V->cols == L->rows, "mb_loss_grad: V has %lld entries for %lld cells",
+           (long long)(V->rows * V->cols), (long long)L->rows);
+  MB_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = L->rows;
+  const int r = (int)L->cols;
+  const int64_t n_cta = std::max<int64_t>(1, min((int64_t)ctx->n_sm, ceil_div64(n, 8)));
+  const int64_t chunks = max(pick_chunks(ctx, n, r), n_cta);
+  PassBuffers pb;
+  MB_TRY(carve(ctx, n, r, chunks, &pb));
+  MB_CUDA(cudaMemcpyAsync(pb.zdev, z_host, (size_t)r * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (n == 0) {
+    MB_CUDA(cudaMemsetAsync(pb.out, 0, (size_t)(r + 1) * sizeof(double), ctx->stream));
+  } else {
+    bool done = false;
+    if (ctx->opt_lossgrad == 0) MB_TRY(launch_fused<false>(ctx, L, pb.zdev, mu, V->p, &pb, n_cta, &done));
+    if (!done) {
+      int nb = 0;
+      MB_TRY(launch_rowdot<MODE_GRAD>(ctx, L, pb.zdev, mu, V->p, pb.wv, pb.lpartial, &nb));
+      MB_TRY(colsum(ctx, L, pb.wv, false, &pb, pick_chunks(ctx, n, r), pb.lpartial, nb));
+    }
+  }
+  MB_TRY(mb_allreduce_raw(ctx, pb.out, r + 1));
+  double* host;
+  MB_TRY(mb_pinned(ctx, (size_t)(r + 1) * sizeof(double), &host));
+  MB_CUDA(cudaMemcpyAsync(host, pb.out, (size_t)(r + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  MB_CUDA(cudaStreamSynchronize(ctx->stream));
+  double zz = 0.0;
+  for (int c = 0; c < r; c++) {
+    zz += z_host[c] * z_host[c];
+    grad_host[c] = z_host[c] + host[c];
+  }
+  // loss = -(prior + likelihood) = 1/2|z|^2 + k/2 log(2 pi) - (sum(f - A) + sum Vdr)
+  *loss = 0.5 * zz + 0.5 * k * 1.8378770664093453 - (host[r] + sum_vdr);
+  return 0;
+}
+
+extern "C" int mb_hess_diag(mb_ctx* ctx, const mb_mat* L, const mb_mat* V, double mu, const double* z_host,
+                            double* diag_host) {
+  MB_CHECK(ctx && L && V && z_host && diag_host, "mb_hess_diag: null argument");
+  MB_CHECK(V->rows * V->cols == L->rows, "mb_hess_diag: V has %lld entries for %lld cells",
+           (long long)(V->rows * V->cols), (long long)L->rows);
+  MB_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = L->rows;
+  const int r = (int)L->cols;
+  const int64_t n_cta = std::max<int64_t>(1, min((int64_t)ctx->n_sm, ceil_div64(n, 8)));
+  const int64_t chunks = max(pick_chunks(ctx, n, r), n_cta);
+  PassBuffers pb;
+  MB_TRY(carve(ctx, n, r, chunks, &pb));
+  MB_CUDA(cudaMemcpyAsync(pb.zdev, z_host, (size_t)r * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (n == 0) {
+    MB_CUDA(cudaMemsetAsync(pb.out, 0, (size_t)(r + 1) * sizeof(double), ctx->stream));
+  } else {
+    bool done = false;
+    if (ctx->opt_lossgrad == 0) MB_TRY(launch_fused<true>(ctx, L, pb.zdev, mu, V->p, &pb, n_cta, &done));
+    if (!done) {
+      MB_TRY(launch_rowdot<MODE_HESS>(ctx, L, pb.zdev, mu, V->p, pb.wv, nullptr, nullptr));
+      MB_TRY(colsum(ctx, L, pb.wv, true, &pb, pick_chunks(ctx, n, r), nullptr, 0));
+    }
+  }
+  MB_TRY(mb_allreduce_raw(ctx, pb.out, r));
+  double* host;
+  MB_TRY(mb_pinned(ctx, (size_t)r * sizeof(double), &host));
+  MB_CUDA(cudaMemcpyAsync(host, pb.out, (size_t)r * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  MB_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int c = 0; c < r; c++) diag_host[c] = 1.0 + host[c];
+  return 0;
+}
+
+// b = L^T t  [all-reduce]
+extern "C" int mb_gemv_t(mb_ctx* ctx, const mb_mat* L, const mb_mat* t, mb_mat* b) {
+  MB_CHECK(ctx && L && t && b, "mb_gemv_t: null argument");
+  MB_CHECK(t->rows * t->cols == L->rows && b->rows * b->cols == L->cols, "mb_gemv_t: shape mismatch");
+  MB_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = L->rows;
+  const int r = (int)L->cols;
+  if (r == 0) return 0;
+  if (n == 0) {
+    MB_TRY(mb_mat_fill(ctx, b, 0.0));
+  } else {
+    int64_t chunks = pick_chunks(ctx, n, r);
+    PassBuffers pb;
+    MB_TRY(carve(ctx, 0, r, chunks, &pb));
+    MB_TRY(colsum(ctx, L, t->p, false, &pb, chunks, nullptr, 0));
+    MB_CUDA(cudaMemcpyAsync(b->p, pb.out, (size_t)r * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  return mb_allreduce_raw(ctx, b->p, r);
+}

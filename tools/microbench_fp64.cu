@@ -1,0 +1,208 @@
+// Microbenchmarks that decide the FP64 kernel design on B200 (sm_100a):
+//   DFMA peak, DMMA (mma.sync f64) peak for m8n8k4 / m16n8k8 / m16n8k16, DFMA+DMMA mixed, HBM copy/write.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench_fp64 microbench_fp64.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
+
+template <int ILP>
+__global__ void dfma_kernel(double* out, int iters, double a, double b) {
+  double acc[ILP];
+#pragma unroll
+  for (int i = 0; i < ILP; i++) acc[i] = threadIdx.x + i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < ILP; i++) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; i++) s += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void dmma1688(double* c, const double* a, const double* b) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+               : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
+}
+__device__ __forceinline__ void dmma16816(double* c, const double* a, const double* b) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, {%12,%13,%14,%15}, {%0,%1,%2,%3};\n"
+               : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+               : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]),
+                 "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]));
+}
+
+template <int ILP>
+__global__ void dmma884_kernel(double* out, int iters, double a, double b) {
+  double c[ILP][2];
+#pragma unroll
+  for (int i = 0; i < ILP; i++) { c[i][0] = threadIdx.x; c[i][1] = i; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < ILP; i++) dmma884(c[i][0], c[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; i++) s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int ILP>
+__global__ void dmma1688_kernel(double* out, int iters, double a, double b) {
+  double c[ILP][4], av[4] = {a, a, b, b}, bv[2] = {b, a};
+#pragma unroll
+  for (int i = 0; i < ILP; i++) { c[i][0] = threadIdx.x; c[i][1] = i; c[i][2] = 1; c[i][3] = 2; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < ILP; i++) dmma1688(c[i], av, bv);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; i++) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int ILP>
+__global__ void dmma16816_kernel(double* out, int iters, double a, double b) {
+  double c[ILP][4], av[8] = {a, a, b, b, a, b, a, b}, bv[4] = {b, a, a, b};
+#pragma unroll
+  for (int i = 0; i < ILP; i++) { c[i][0] = threadIdx.x; c[i][1] = i; c[i][2] = 1; c[i][3] = 2; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < ILP; i++) dmma16816(c[i], av, bv);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; i++) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// mixed: NM dmma884 + NF dfma per iteration, independent chains
+template <int NM, int NF>
+__global__ void mixed_kernel(double* out, int iters, double a, double b) {
+  double c[NM + 1][2], f[NF + 1];
+#pragma unroll
+  for (int i = 0; i < NM; i++) { c[i][0] = threadIdx.x; c[i][1] = i; }
+#pragma unroll
+  for (int i = 0; i < NF; i++) f[i] = threadIdx.x + i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < NM; i++) dmma884(c[i][0], c[i][1], a, b);
+#pragma unroll
+    for (int i = 0; i < NF; i++) f[i] = fma(f[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < NM; i++) s += c[i][0] + c[i][1];
+#pragma unroll
+  for (int i = 0; i < NF; i++) s += f[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// exp / sqrt throughput
+__global__ void exp_kernel(double* out, int iters, double a) {
+  double x[4] = {a + threadIdx.x * 1e-3, a * 2, a * 3, a * 4}, s = 0;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) { s += exp(-x[i]); x[i] += 1e-6; }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void sqrt_kernel(double* out, int iters, double a) {
+  double x[4] = {a + threadIdx.x * 1e-3, a * 2, a * 3, a * 4}, s = 0;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) { s += sqrt(x[i]); x[i] += 1e-6; }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void copy_kernel(const double2* __restrict__ in, double2* __restrict__ out, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) out[i] = in[i];
+}
+__global__ void write_kernel(double2* __restrict__ out, size_t n, double v) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) out[i] = make_double2(v, v);
+}
+__global__ void read_kernel(const double2* __restrict__ in, double* out, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  double s = 0;
+  for (; i < n; i += st) { double2 v = in[i]; s += v.x + v.y; }
+  if (s == 123.456) out[0] = s;
+}
+
+template <class F>
+float timeit(F f, int reps = 5) {
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  f(); CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int r = 0; r < reps; r++) {
+    CK(cudaEventRecord(e0)); f(); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
+  }
+  return best;
+}
+
+int main() {
+  cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+  int sm = p.multiProcessorCount;
+  printf("device %s, %d SMs, cc %d.%d\n", p.name, sm, p.major, p.minor);
+  double* out; CK(cudaMalloc(&out, sizeof(double) * sm * 8 * 1024));
+  const int iters = 20000;
+  for (int warps : {4, 8, 16, 32}) {
+    int threads = warps * 32;
+    dim3 g(sm), b(threads);
+    float ms = timeit([&] { dfma_kernel<16><<<g, b>>>(out, iters, 1.0000001, 1e-9); });
+    double fl = 2.0 * 16 * iters * (double)threads * sm;
+    printf("DFMA       warps/SM=%2d: %8.2f TFLOP/s\n", warps, fl / ms * 1e-9);
+    ms = timeit([&] { dmma884_kernel<16><<<g, b>>>(out, iters, 1.0000001, 1e-9); });
+    fl = 2.0 * 256 * 16 * iters * (double)warps * sm;
+    printf("DMMA 884   warps/SM=%2d: %8.2f TFLOP/s\n", warps, fl / ms * 1e-9);
+    ms = timeit([&] { dmma1688_kernel<8><<<g, b>>>(out, iters, 1.0000001, 1e-9); });
+    fl = 2.0 * 1024 * 8 * iters * (double)warps * sm;
+    printf("DMMA 1688  warps/SM=%2d: %8.2f TFLOP/s\n", warps, fl / ms * 1e-9);
+    ms = timeit([&] { dmma16816_kernel<8><<<g, b>>>(out, iters, 1.0000001, 1e-9); });
+    fl = 2.0 * 2048 * 8 * iters * (double)warps * sm;
+    printf("DMMA 16816 warps/SM=%2d: %8.2f TFLOP/s\n", warps, fl / ms * 1e-9);
+  }
+  {
+    dim3 g(sm), b(512);
+    float ms = timeit([&] { mixed_kernel<8, 8><<<g, b>>>(out, iters, 1.0000001, 1e-9); });
+    double fl_m = 2.0 * 256 * 8 * iters * 16.0 * sm, fl_f = 2.0 * 8 * iters * 512.0 * sm;
+    printf("MIXED 8 dmma884 + 8 dfma / iter (16 warps): %.3f ms  -> DMMA %.2f TF + DFMA %.2f TF = %.2f TF\n", ms,
+           fl_m / ms * 1e-9, fl_f / ms * 1e-9, (fl_m + fl_f) / ms * 1e-9);
+    ms = timeit([&] { mixed_kernel<8, 32><<<g, b>>>(out, iters, 1.0000001, 1e-9); });
+    fl_f = 2.0 * 32 * iters * 512.0 * sm;
+    printf("MIXED 8 dmma884 + 32 dfma / iter (16 warps): %.3f ms -> DMMA %.2f TF + DFMA %.2f TF = %.2f TF\n", ms,
+           fl_m / ms * 1e-9, fl_f / ms * 1e-9, (fl_m + fl_f) / ms * 1e-9);
+    ms = timeit([&] { mixed_kernel<8, 0><<<g, b>>>(out, iters, 1.0000001, 1e-9); });
+    printf("ONLY  8 dmma884 / iter (16 warps): %.3f ms -> %.2f TF\n", ms, fl_m / ms * 1e-9);
+    ms = timeit([&] { mixed_kernel<0, 32><<<g, b>>>(out, iters, 1.0000001, 1e-9); });
+    printf("ONLY  32 dfma / iter (16 warps): %.3f ms -> %.2f TF\n", ms, fl_f / ms * 1e-9);
+  }
+  {
+    dim3 g(sm * 2), b(512);
+    int it2 = 2000;
+    float ms = timeit([&] { exp_kernel<<<g, b>>>(out, it2, 0.37); });
+    printf("exp():  %.2f G evals/s\n", 4.0 * it2 * 512.0 * sm * 2 / ms * 1e-6);
+    ms = timeit([&] { sqrt_kernel<<<g, b>>>(out, it2, 0.37); });
+    printf("sqrt(): %.2f G evals/s\n", 4.0 * it2 * 512.0 * sm * 2 / ms * 1e-6);
+  }
+  {
+    size_t bytes = (size_t)8 << 30;  // 8 GiB each
+    double2 *a, *b2; CK(cudaMalloc(&a, bytes)); CK(cudaMalloc(&b2, bytes));
+    CK(cudaMemset(a, 0, bytes)); CK(cudaMemset(b2, 0, bytes));
+    size_t n = bytes / sizeof(double2);
+    float ms = timeit([&] { copy_kernel<<<sm * 16, 512>>>(a, b2, n); });
+    printf("HBM copy  (r+w): %.1f GB/s\n", 2.0 * bytes / ms * 1e-6);
+    ms = timeit([&] { write_kernel<<<sm * 16, 512>>>(b2, n, 1.0); });
+    printf("HBM write      : %.1f GB/s\n", 1.0 * bytes / ms * 1e-6);
+    ms = timeit([&] { read_kernel<<<sm * 16, 512>>>(a, out, n); });
+    printf("HBM read       : %.1f GB/s\n", 1.0 * bytes / ms * 1e-6);
+    ms = timeit([&] { CK(cudaMemsetAsync(b2, 0, bytes)); });
+    printf("cudaMemset     : %.1f GB/s\n", 1.0 * bytes / ms * 1e-6);
+  }
+  return 0;
+}
