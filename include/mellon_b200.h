@@ -90,6 +90,15 @@ int64_t mb_ctx_launch_count(mb_ctx* ctx);
  * `slot` in [0, 16) lets several intervals be open at once. */
 int mb_timer_start(mb_ctx* ctx, int slot);
 int mb_timer_stop(mb_ctx* ctx, int slot, double* ms);
+/* per-kernel-class stopwatch: while enabled, every launch of a class is bracketed by CUDA
+ * events on the context's stream; mb_prof_read returns the launch count and summed device
+ * time since the last reset, plus the ALGORITHMIC work of those launches (`work`: bytes for the
+ * HBM-bound classes, flops for the GEMM class).  Classes: 0 = K1 covariance build (x != y),
+ * 1 = K7 covariance mat-vec, 2 = FP64 GEMM tiles (K3/K4/K2 updates), 3 = K5/K6 fused objective
+ * pass, 4 = everything else that is timed (the symmetric landmark covariance K_MM). */
+int mb_prof_enable(mb_ctx* ctx, int on);
+int mb_prof_reset(mb_ctx* ctx);
+int mb_prof_read(mb_ctx* ctx, int cls, int64_t* count, double* ms, double* work);
 /* overwrite a scratch buffer larger than L2 (cache flush between timed iterations) */
 int mb_flush_l2(mb_ctx* ctx);
 /* select kernel variants for A/B measurements ("gemm", "cov", "lossgrad") */
@@ -128,6 +137,11 @@ int mb_mat_scale_cols(mb_ctx* ctx, mb_mat* a, const mb_mat* s);
 int mb_mat_copy_cols(mb_ctx* ctx, const mb_mat* src, int64_t c0, int64_t ncols, mb_mat* dst);
 /* copy the lower triangle onto the upper one (symmetrise a lower-only result) */
 int mb_mat_symmetrize(mb_ctx* ctx, mb_mat* a);
+/* a *= s                          conditional.py:139-181 (`A / sigma2`), :296-300 */
+int mb_mat_scale(mb_ctx* ctx, mb_mat* a, double s);
+/* out(i) = sum_j a(i, j)^2        conditional.py:417,436,712,731,941,959 (`arraysum(square(A), axis=0)`
+ * on the transposed layout this library keeps) */
+int mb_mat_row_sumsq(mb_ctx* ctx, const mb_mat* a, mb_mat* out);
 
 /* ---- K1: fused pairwise distance + covariance kernel -----------------------------------
  * K(i, j) = prog(x_i, y_j); replaces util.py:351-366 (distance) + cov.py `k` methods +
@@ -136,6 +150,13 @@ int mb_mat_symmetrize(mb_ctx* ctx, mb_mat* a);
 int mb_cov_build(mb_ctx* ctx, const mb_kprog* prog, const mb_mat* x, const mb_mat* y, mb_mat* K);
 /* diag(i) = prog(x_i, x_i)        base_cov.py:71-93 */
 int mb_cov_diag(mb_ctx* ctx, const mb_kprog* prog, const mb_mat* x, mb_mat* out);
+
+/* ---- exact nearest neighbour (the step before the path) ------------------
+ * dist(i) = min_{j != i + self_offset} |x_i - all_j| and its index: brute force over the same
+ * distance tiles as K1 with a running-minimum epilogue, then the selected pair's distance is
+ * recomputed as sqrt(sum (x - y)^2).  Replaces parameters.py:352-433 (pynndescent k=1). */
+int mb_nn_distances(mb_ctx* ctx, const mb_mat* x, const mb_mat* all, int64_t self_offset, mb_mat* dist,
+                    int64_t* idx_host);
 
 /* ---- K7: fused covariance + mat-vec (never materialises K) -----------------------------
  * out = mu + prog(xq, base) @ w ; w is (m, p), out is (nq, p).

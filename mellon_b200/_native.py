@@ -70,6 +70,9 @@ SIGNATURES = {
     "mb_ctx_launch_count": (_i64, [_vp]),
     "mb_timer_start": (_i, [_vp, _i]),
     "mb_timer_stop": (_i, [_vp, _i, _pd]),
+    "mb_prof_enable": (_i, [_vp, _i]),
+    "mb_prof_reset": (_i, [_vp]),
+    "mb_prof_read": (_i, [_vp, _i, C.POINTER(_i64), _pd, _pd]),
     "mb_flush_l2": (_i, [_vp]),
     "mb_set_option": (_i, [_vp, C.c_char_p, _i]),
     "mb_host_alloc": (_i, [_i64, C.POINTER(_vp)]),
@@ -92,8 +95,11 @@ SIGNATURES = {
     "mb_mat_scale_cols": (_i, [_vp, _vp, _vp]),
     "mb_mat_copy_cols": (_i, [_vp, _vp, _i64, _i64, _vp]),
     "mb_mat_symmetrize": (_i, [_vp, _vp]),
+    "mb_mat_scale": (_i, [_vp, _vp, _d]),
+    "mb_mat_row_sumsq": (_i, [_vp, _vp, _vp]),
     "mb_cov_build": (_i, [_vp, _pprog, _vp, _vp, _vp]),
     "mb_cov_diag": (_i, [_vp, _pprog, _vp, _vp]),
+    "mb_nn_distances": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "mb_cov_matvec": (_i, [_vp, _pprog, _vp, _vp, _vp, _d, _vp]),
     "mb_predict_mean": (_i, [_vp, _pprog, _vp, _i64, _i64, _vp, _vp, _d, _vp]),
     "mb_potrf": (_i, [_vp, _vp]),

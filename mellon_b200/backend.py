@@ -149,6 +149,9 @@ class CudaBackend:
                 raise ValueError("world > 1 needs the 128-byte NCCL unique id of rank 0")
             nat.check(self.lib.mb_comm_init(self.ctx, bytes(unique_id), rank, world), "mb_comm_init")
         self._progs = {}
+        # host<->device traffic of the calls made through this object (bench.py's e2e accounting)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
 
     # -- construction ------------------------------------------------------------------------
     @classmethod
@@ -189,6 +192,23 @@ class CudaBackend:
         ms = C.c_double()
         nat.check(self.lib.mb_timer_stop(self.ctx, slot, C.byref(ms)))
         return ms.value
+
+    PROF_CLASSES = {"cov": 0, "matvec": 1, "gemm": 2, "lossgrad": 3, "other": 4}
+
+    def prof_enable(self, on=True):
+        nat.check(self.lib.mb_prof_enable(self.ctx, int(bool(on))), "mb_prof_enable")
+
+    def prof_reset(self):
+        nat.check(self.lib.mb_prof_reset(self.ctx), "mb_prof_reset")
+
+    def prof_read(self):
+        """{class: (launches, device ms, algorithmic bytes or flops)} since the last reset."""
+        out = {}
+        for name, cls in self.PROF_CLASSES.items():
+            n, ms, work = C.c_int64(), C.c_double(), C.c_double()
+            nat.check(self.lib.mb_prof_read(self.ctx, cls, C.byref(n), C.byref(ms), C.byref(work)), "mb_prof_read")
+            out[name] = (n.value, ms.value, work.value)
+        return out
 
     def flush_l2(self):
         nat.check(self.lib.mb_flush_l2(self.ctx))
@@ -239,6 +259,7 @@ class CudaBackend:
             d = self.empty(n, a2.shape[1], global_rows=n if sharded else None, vector=vector)
         if blk.size:
             nat.check(self.lib.mb_mat_upload(self.ctx, d._h, nat.ptr(blk), 0, blk.shape[0]), "mb_mat_upload")
+            self.h2d_bytes += blk.nbytes
         return d
 
     def _download_local(self, d):
@@ -246,6 +267,7 @@ class CudaBackend:
         out = np.empty((rows, cols), dtype=np.float64)
         if out.size:
             nat.check(self.lib.mb_mat_download(self.ctx, d._h, nat.ptr(out), 0, rows), "mb_mat_download")
+            self.d2h_bytes += out.nbytes
         return out
 
     def download(self, d):
@@ -308,6 +330,24 @@ class CudaBackend:
                        row_lo=xd.row_lo)
         nat.check(self.lib.mb_cov_build(self.ctx, C.byref(prog.struct), xd._h, yd._h, K._h), "mb_cov_build")
         return K
+
+    def nn_distances(self, x, return_index=False):
+        """Exact nearest-neighbour distance of every row of ``x`` (brute force on the device).
+        With a communicator each rank searches its row block against all points."""
+        x = np.asarray(x, dtype=np.float64)
+        x2 = x.reshape(-1, 1) if x.ndim == 1 else x
+        n = x2.shape[0]
+        alld = self.upload(x2)
+        lo, hi, _ = row_block(n, self.rank, self.world) if self.world > 1 else (0, n, n)
+        blk = alld if self.world == 1 else self.upload(np.ascontiguousarray(x2[lo:hi]))
+        dist = self.empty(hi - lo, 1, vector=True)
+        idx = np.empty(hi - lo, dtype=np.int64)
+        nat.check(self.lib.mb_nn_distances(self.ctx, blk._h, alld._h, lo, dist._h, nat.ptr(idx)), "mb_nn_distances")
+        out = self._download_local(dist)[:, 0]
+        if self.world > 1:
+            out = self.gather_rows(out, n)
+            idx = self.gather_rows(idx.astype(np.float64), n).astype(np.int64)
+        return (out, idx) if return_index else out
 
     def cov_diag(self, cov_func, x):
         xd = self.upload(x)
@@ -382,10 +422,14 @@ class CudaBackend:
         td = self.upload(np.asarray(target, dtype=np.float64), sharded=L.sharded)
         z0 = np.empty(L.local_shape[1], dtype=np.float64)
         nat.check(self.lib.mb_ridge_init(self.ctx, L._h, td._h, nat.ptr(z0)), "mb_ridge_init")
+        self.d2h_bytes += z0.nbytes
         return z0
 
-    def gemm(self, A, B, trans_a=False, trans_b=False, alpha=1.0, beta=0.0, out=None):
-        A, B = self.upload(A), self.upload(B)
+    def gemm(self, A, B, trans_a=False, trans_b=False, alpha=1.0, beta=0.0, out=None, reduce=False):
+        """``alpha op(A) op(B) + beta out``.  ``reduce``: both operands are row-sharded and contracted
+        over the cell axis (op(A) = A^T) — the partial products are all-reduced."""
+        A = self.upload(A)
+        B = self.upload(B, sharded=reduce)
         m = A.local_shape[1] if trans_a else A.local_shape[0]
         n = B.local_shape[0] if trans_b else B.local_shape[1]
         if out is None:
@@ -393,7 +437,30 @@ class CudaBackend:
             out = self.empty(m, n, global_rows=A.shape[0] if keep_rows else None, row_lo=A.row_lo if keep_rows else 0)
         nat.check(self.lib.mb_gemm(self.ctx, int(trans_a), int(trans_b), float(alpha), A._h, B._h, float(beta),
                                    out._h), "mb_gemm")
+        if reduce:
+            self.allreduce(out)
         return out
+
+    def eye(self, n):
+        out = self.empty(n, n)
+        nat.check(self.lib.mb_mat_fill(self.ctx, out._h, 0.0), "mb_mat_fill")
+        return self.add_diag(out, 1.0)
+
+    def copy(self, A):
+        out = self.empty(*A.local_shape, global_rows=A.shape[0] if A.sharded else None, row_lo=A.row_lo,
+                         vector=A._vector)
+        nat.check(self.lib.mb_mat_copy(self.ctx, A._h, out._h), "mb_mat_copy")
+        return out
+
+    def scale(self, A, s):
+        nat.check(self.lib.mb_mat_scale(self.ctx, A._h, float(s)), "mb_mat_scale")
+        return A
+
+    def row_sumsq(self, A):
+        """Host vector of the squared row norms of a (non-sharded or local) device matrix."""
+        out = self.empty(A.local_shape[0], 1, vector=True)
+        nat.check(self.lib.mb_mat_row_sumsq(self.ctx, A._h, out._h), "mb_mat_row_sumsq")
+        return self._download_local(out)[:, 0]
 
     def allreduce(self, A):
         nat.check(self.lib.mb_comm_allreduce(self.ctx, A._h), "mb_comm_allreduce")
@@ -436,12 +503,16 @@ class CudaBackend:
         grad = np.empty_like(z)
         nat.check(self.lib.mb_loss_grad(self.ctx, st.L._h, st.V._h, st.sum_vdr, st.mu, st.k, nat.ptr(z),
                                         C.byref(loss), nat.ptr(grad)), "mb_loss_grad")
+        self.h2d_bytes += z.nbytes
+        self.d2h_bytes += grad.nbytes + 8
         return loss.value, grad
 
     def hess_diag(self, st, z):
         z = nat.as_f64(z)
         out = np.empty_like(z)
         nat.check(self.lib.mb_hess_diag(self.ctx, st.L._h, st.V._h, st.mu, nat.ptr(z), nat.ptr(out)), "mb_hess_diag")
+        self.h2d_bytes += z.nbytes
+        self.d2h_bytes += out.nbytes
         return out
 
     def transform(self, L, z, mu):
@@ -452,6 +523,8 @@ class CudaBackend:
             raise ValueError(f"z has shape {z.shape}, L has rank {Ld.local_shape[1]}")
         f = np.empty(Ld.local_shape[0], dtype=np.float64)
         nat.check(self.lib.mb_transform(self.ctx, Ld._h, nat.ptr(z), float(mu), nat.ptr(f)), "mb_transform")
+        self.h2d_bytes += z.nbytes
+        self.d2h_bytes += f.nbytes
         if Ld.sharded and self.world > 1:
             return self.gather_rows(f, Ld.shape[0])
         return f
@@ -478,6 +551,8 @@ class CudaBackend:
         out = np.empty((hi - lo, wd.local_shape[1]), dtype=np.float64)
         nat.check(self.lib.mb_predict_mean(self.ctx, C.byref(prog.struct), nat.ptr(blk), hi - lo, blk.shape[1],
                                            based._h, wd._h, float(mu), nat.ptr(out)), "mb_predict_mean")
+        self.h2d_bytes += blk.nbytes
+        self.d2h_bytes += out.nbytes
         if self.world > 1:
             out = self.gather_rows(out, n)
         return out[:, 0] if vec else out

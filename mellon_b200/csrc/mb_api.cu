@@ -13,6 +13,7 @@ void mb_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* mb_last_error(void) { return g_err; }
+static int prof_resolve(mb_ctx* c);
 extern "C" int mb_version(void) { return 100; }
 
 extern "C" int mb_device_count(int* n) {
@@ -37,7 +38,6 @@ extern "C" int mb_ctx_create(int device, mb_ctx** out) {
   MB_CHECK(prop.major >= 10, "mb_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
            device, prop.major, prop.minor);
   mb_ctx* c = new mb_ctx();
-  memset(c, 0, sizeof(*c));
   c->device = device;
   c->n_sm = prop.multiProcessorCount;
   MB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -60,6 +60,8 @@ extern "C" int mb_ctx_destroy(mb_ctx* c) {
   if (c->scratch) cudaFree(c->scratch);
   if (c->flush_buf) cudaFree(c->flush_buf);
   if (c->pinned) cudaFreeHost(c->pinned);
+  prof_resolve(c);
+  for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   for (int i = 0; i < 16; i++)
     for (int j = 0; j < 2; j++) cudaEventDestroy(c->timer_ev[i][j]);
   cudaEventDestroy(c->ev_a);
@@ -104,6 +106,63 @@ extern "C" int mb_timer_stop(mb_ctx* c, int slot, double* ms) {
   float f = 0;
   MB_CUDA(cudaEventElapsedTime(&f, c->timer_ev[slot][0], c->timer_ev[slot][1]));
   *ms = f;
+  return 0;
+}
+
+cudaEvent_t mb_prof_event(mb_ctx* c) {
+  if (!c->prof_pool.empty()) {
+    cudaEvent_t e = c->prof_pool.back();
+    c->prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+static int prof_resolve(mb_ctx* c) {
+  if (c->prof_spans.empty()) return 0;
+  MB_CUDA(cudaStreamSynchronize(c->stream));
+  for (const mb_prof_span& sp : c->prof_spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+      c->prof_count[sp.cls]++;
+      c->prof_ms[sp.cls] += ms;
+    }
+    c->prof_pool.push_back(sp.a);
+    c->prof_pool.push_back(sp.b);
+  }
+  c->prof_spans.clear();
+  return 0;
+}
+
+extern "C" int mb_prof_enable(mb_ctx* c, int on) {
+  MB_CHECK(c, "mb_prof_enable: null ctx");
+  MB_CUDA(cudaSetDevice(c->device));
+  MB_TRY(prof_resolve(c));
+  c->prof_on = on != 0;
+  return 0;
+}
+
+extern "C" int mb_prof_reset(mb_ctx* c) {
+  MB_CHECK(c, "mb_prof_reset: null ctx");
+  MB_CUDA(cudaSetDevice(c->device));
+  MB_TRY(prof_resolve(c));
+  for (int i = 0; i < MB_PROF_NCLS; i++) {
+    c->prof_count[i] = 0;
+    c->prof_ms[i] = 0.0;
+    c->prof_work[i] = 0.0;
+  }
+  return 0;
+}
+
+extern "C" int mb_prof_read(mb_ctx* c, int cls, int64_t* count, double* ms, double* work) {
+  MB_CHECK(c && cls >= 0 && cls < MB_PROF_NCLS, "mb_prof_read: bad class %d", cls);
+  MB_CUDA(cudaSetDevice(c->device));
+  MB_TRY(prof_resolve(c));
+  if (count) *count = c->prof_count[cls];
+  if (ms) *ms = c->prof_ms[cls];
+  if (work) *work = c->prof_work[cls];
   return 0;
 }
 
@@ -200,6 +259,25 @@ __global__ void k_symmetrize(double* a, int64_t n) {
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     int64_t r = c0 + j, c = r0 + threadIdx.x;  // transposed position
     if (r < n && c < n && c > r) a[r * n + c] = tile[threadIdx.x][j];
+  }
+}
+
+__global__ void k_scale(double* a, int64_t n, double s) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) a[i] *= s;
+}
+
+// one warp per row, fixed-order lane sums + shuffle tree
+__global__ void k_row_sumsq(const double* __restrict__ a, int64_t rows, int64_t cols, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < rows; i += nwarps) {
+    const double* row = a + i * cols;
+    double s = 0.0;
+    for (int64_t c = lane; c < cols; c += 32) s = fma(row[c], row[c], s);
+    s = warp_sum(s);
+    if (lane == 0) out[i] = s;
   }
 }
 
@@ -375,5 +453,27 @@ extern "C" int mb_mat_symmetrize(mb_ctx* c, mb_mat* a) {
   if (a->rows == 0) return 0;
   unsigned t = (unsigned)ceil_div64(a->rows, 32);
   MB_LAUNCH(c, k_symmetrize, dim3(t, t), dim3(32, 8), 0, a->p, a->rows);
+  return 0;
+}
+
+extern "C" int mb_mat_scale(mb_ctx* c, mb_mat* a, double s) {
+  MB_CHECK(c && a, "mb_mat_scale: null argument");
+  MB_CUDA(cudaSetDevice(c->device));
+  int64_t n = a->rows * a->cols;
+  if (n == 0) return 0;
+  int grid = (int)min((int64_t)c->n_sm * 8, ceil_div64(n, 256));
+  MB_LAUNCH(c, k_scale, grid, 256, 0, a->p, n, s);
+  return 0;
+}
+
+extern "C" int mb_mat_row_sumsq(mb_ctx* c, const mb_mat* a, mb_mat* out) {
+  MB_CHECK(c && a && out, "mb_mat_row_sumsq: null argument");
+  MB_CHECK(out->rows * out->cols == a->rows, "mb_mat_row_sumsq: output has %lld entries for %lld rows",
+           (long long)(out->rows * out->cols), (long long)a->rows);
+  MB_CUDA(cudaSetDevice(c->device));
+  if (a->rows == 0) return 0;
+  if (a->cols == 0) return mb_mat_fill(c, out, 0.0);
+  int grid = (int)min((int64_t)c->n_sm * 8, ceil_div64(a->rows, 8));
+  MB_LAUNCH(c, k_row_sumsq, grid, 256, 0, a->p, a->rows, a->cols, out->p);
   return 0;
 }

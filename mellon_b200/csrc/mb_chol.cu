@@ -108,6 +108,69 @@ int potrf_rec(mb_ctx* ctx, double* A, int64_t lda, int64_t off, int64_t n, int* 
   return potrf_rec(ctx, A, lda, off + n1, n2, info);
 }
 
+// ---- leaf: B[0:w, :] <- T^-1 B (trans = 0) or T^-T B (trans = 1), T (w <= 32) lower ----------
+// one thread per right-hand-side column (coalesced across the row), the column in registers.
+__global__ void __launch_bounds__(128)
+trsm_left_leaf_kernel(const double* __restrict__ T, int64_t ldt, int w, int trans, double* __restrict__ B,
+                      int64_t ldb, int64_t nrhs) {
+  __shared__ double Ts[NB][NB + 1];
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    int r = e / NB, c = e % NB;
+    Ts[r][c] = (r < w && c < w) ? T[r * ldt + c] : (r == c ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  const int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (col >= nrhs) return;
+  double x[NB];
+#pragma unroll
+  for (int r = 0; r < NB; r++) x[r] = (r < w) ? B[r * ldb + col] : 0.0;
+  if (!trans) {
+#pragma unroll
+    for (int r = 0; r < NB; r++) {
+      double s = x[r];
+#pragma unroll
+      for (int k = 0; k < r; k++) s = fma(-Ts[r][k], x[k], s);
+      x[r] = s / Ts[r][r];
+    }
+  } else {
+#pragma unroll
+    for (int r = NB - 1; r >= 0; r--) {
+      double s = x[r];
+#pragma unroll
+      for (int k = r + 1; k < NB; k++) s = fma(-Ts[k][r], x[k], s);
+      x[r] = s / Ts[r][r];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < NB; r++)
+    if (r < w) B[r * ldb + col] = x[r];
+}
+
+// B[r0:r0+w, :] <- L[r0:r0+w, r0:r0+w]^-1 (or ^-T) B[r0:r0+w, :], recursive with GEMM updates
+int trsm_left_rec(mb_ctx* ctx, const double* L, int64_t ldl, int64_t r0, int64_t w, int trans, double* B,
+                  int64_t ldb, int64_t nrhs) {
+  if (w <= 0) return 0;
+  if (w <= NB) {
+    MB_LAUNCH(ctx, trsm_left_leaf_kernel, (int)ceil_div64(nrhs, 128), 128, 0, L + r0 * ldl + r0, ldl, (int)w,
+              trans, B + r0 * ldb, ldb, nrhs);
+    return 0;
+  }
+  const int64_t w1 = ((w / 2 + NB - 1) / NB) * NB, w2 = w - w1;
+  const double* L21 = L + (r0 + w1) * ldl + r0;
+  if (!trans) {
+    MB_TRY(trsm_left_rec(ctx, L, ldl, r0, w1, trans, B, ldb, nrhs));
+    // B2 -= L21 B1
+    MB_TRY(mb_gemm_raw(ctx, false, true, w2, nrhs, w1, -1.0, L21, ldl, B + r0 * ldb, ldb, 1.0,
+                       B + (r0 + w1) * ldb, ldb, false));
+    return trsm_left_rec(ctx, L, ldl, r0 + w1, w2, trans, B, ldb, nrhs);
+  }
+  MB_TRY(trsm_left_rec(ctx, L, ldl, r0 + w1, w2, trans, B, ldb, nrhs));
+  // B1 -= L21^T B2
+  MB_TRY(mb_gemm_raw(ctx, true, true, w1, nrhs, w2, -1.0, L21, ldl, B + (r0 + w1) * ldb, ldb, 1.0, B + r0 * ldb,
+                     ldb, false));
+  return trsm_left_rec(ctx, L, ldl, r0, w1, trans, B, ldb, nrhs);
+}
+
 __global__ void zero_upper_kernel(double* a, int64_t n, int64_t lda) {
   int64_t i = blockIdx.y, j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n && j < n && j > i) a[i * lda + j] = 0.0;
@@ -233,12 +296,6 @@ extern "C" int mb_tri_solve(mb_ctx* ctx, const mb_mat* Lp, int trans, mb_mat* B)
     MB_LAUNCH(ctx, trsv_kernel, (int)nrhs, 1024, smem, Lp->p, Lp->cols, (int)m, B->p, (int)nrhs, trans);
     return 0;
   }
-  // wide right-hand sides: (Lp^-1 B)^T = B^T Lp^-T  -> transpose, right-side solve, transpose back
-  MB_CHECK(!trans, "mb_tri_solve: transposed solve supports at most 64 right-hand sides and m <= 25600");
-  double* scratch;
-  MB_TRY(mb_scratch(ctx, (size_t)m * nrhs * sizeof(double), &scratch));
-  mb_mat bt = {scratch, nrhs, m, ctx, false};
-  MB_TRY(mb_mat_transpose(ctx, B, &bt));
-  MB_TRY(mb_trsm_right_lt_raw(ctx, Lp->p, Lp->cols, m, bt.p, m, nrhs));
-  return mb_mat_transpose(ctx, &bt, B);
+  // wide right-hand sides: blocked left solve, the O(m^2 nrhs) work in the DMMA GEMM
+  return trsm_left_rec(ctx, Lp->p, Lp->cols, 0, m, trans ? 1 : 0, B->p, nrhs, nrhs);
 }

@@ -18,29 +18,47 @@ struct mb_mat {
   bool owns;
 };
 
-struct mb_ctx {
-  int device;
-  int n_sm;
-  cudaStream_t stream;       // compute stream (everything is ordered on it)
-  cudaStream_t copy_stream;  // H2D/D2H overlap for the streaming predictor
-  cudaEvent_t timer_ev[16][2];
-  cudaEvent_t ev_a, ev_b;
-  int64_t launches;
-  // scratch
-  double* scratch;           // reusable device scratch
-  size_t scratch_bytes;
-  double* pinned;            // reusable pinned host staging
-  size_t pinned_bytes;
-  double* flush_buf;
-  size_t flush_bytes;
-  // NCCL
-  void* comm;
-  int rank, world;
-  // options
-  int opt_gemm;      // 0 = DMMA tiles (default), 1 = DFMA register tiles
-  int opt_cov;       // 0 = default tile kernel
-  int opt_lossgrad;  // 0 = fused single pass, 1 = two-pass
+// kernel classes for the in-library stopwatch (mb_prof_*): CUDA events around each launch
+enum { MB_PROF_COV = 0, MB_PROF_MATVEC = 1, MB_PROF_GEMM = 2, MB_PROF_LOSSGRAD = 3, MB_PROF_OTHER = 4,
+       MB_PROF_NCLS = 5 };
+
+struct mb_prof_span {
+  int cls;
+  cudaEvent_t a, b;
 };
+
+struct mb_ctx {
+  int device = 0;
+  int n_sm = 0;
+  cudaStream_t stream = nullptr;       // compute stream (everything is ordered on it)
+  cudaStream_t copy_stream = nullptr;  // H2D/D2H overlap for the streaming predictor
+  cudaEvent_t timer_ev[16][2] = {};
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  int64_t launches = 0;
+  // scratch
+  double* scratch = nullptr;           // reusable device scratch
+  size_t scratch_bytes = 0;
+  double* pinned = nullptr;            // reusable pinned host staging
+  size_t pinned_bytes = 0;
+  double* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+  // NCCL
+  void* comm = nullptr;
+  int rank = 0, world = 1;
+  // options
+  int opt_gemm = 0;      // 0 = DMMA tiles (default), 1 = DFMA register tiles
+  int opt_cov = 0;       // 0 = default tile kernel
+  int opt_lossgrad = 0;  // 0 = fused single pass, 1 = two-pass
+  // per-kernel-class stopwatch
+  bool prof_on = false;
+  std::vector<mb_prof_span> prof_spans;      // recorded, not yet resolved
+  std::vector<cudaEvent_t> prof_pool;        // recycled events
+  int64_t prof_count[MB_PROF_NCLS] = {};
+  double prof_ms[MB_PROF_NCLS] = {};
+  double prof_work[MB_PROF_NCLS] = {};  // algorithmic bytes (HBM-bound classes) or flops (GEMM)
+};
+
+cudaEvent_t mb_prof_event(mb_ctx* ctx);
 
 void mb_set_error(const char* fmt, ...);
 
@@ -74,6 +92,24 @@ void mb_set_error(const char* fmt, ...);
   do {                                                                             \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);               \
     (ctx)->launches++;                                                             \
+    MB_CUDA(cudaGetLastError());                                                   \
+  } while (0)
+
+// Same, with the launch bracketed by CUDA events on the stream when profiling is on.
+#define MB_LAUNCH_P(ctx, cls, kernel, grid, block, smem, ...)                      \
+  do {                                                                             \
+    mb_prof_span _sp = {(cls), nullptr, nullptr};                                  \
+    if ((ctx)->prof_on) {                                                          \
+      _sp.a = mb_prof_event(ctx);                                                  \
+      _sp.b = mb_prof_event(ctx);                                                  \
+      cudaEventRecord(_sp.a, (ctx)->stream);                                       \
+    }                                                                              \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);               \
+    (ctx)->launches++;                                                             \
+    if ((ctx)->prof_on) {                                                          \
+      cudaEventRecord(_sp.b, (ctx)->stream);                                       \
+      (ctx)->prof_spans.push_back(_sp);                                            \
+    }                                                                              \
     MB_CUDA(cudaGetLastError());                                                   \
   } while (0)
 

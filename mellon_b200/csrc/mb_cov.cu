@@ -16,7 +16,7 @@
 namespace {
 
 constexpr int BM = 128, BN = 64, NT = 256;
-enum { MODE_STORE = 0, MODE_MATVEC = 1 };
+enum { MODE_STORE = 0, MODE_MATVEC = 1, MODE_NNMIN = 2 };
 
 struct LeafParams {
   int kind;
@@ -244,13 +244,15 @@ template <int KIND, int MODE>
 __global__ void __launch_bounds__(NT, 1)
 cov_tile_kernel(const double* __restrict__ xp, const double* __restrict__ xnorm, int64_t n,
                 const double* __restrict__ yp, const double* __restrict__ ynorm, int64_t m, int ldp,
-                LeafParams par, double* __restrict__ out, int64_t ldo, const double* __restrict__ w, double mu) {
+                LeafParams par, double* __restrict__ out, int64_t ldo, const double* __restrict__ w, double mu,
+                int64_t self_offset = 0, int64_t* __restrict__ nn_idx = nullptr) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* xs = reinterpret_cast<double*>(smem_raw);
   double* ys0 = xs + (size_t)BM * ldp;
   double* ys1 = ys0 + (size_t)BN * ldp;
   __shared__ __align__(8) uint64_t bar_x, bar_y[2];
   __shared__ double mv_red[2][BM];
+  __shared__ int64_t nn_red[2][BM];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = lane & 7, ty = lane >> 3;
@@ -290,8 +292,12 @@ cov_tile_kernel(const double* __restrict__ xp, const double* __restrict__ xnorm,
       xn[i] = (r < n) ? xnorm[r] : 0.0;
     }
     double rowacc[8];
+    int64_t rowidx[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) rowacc[i] = 0.0;
+    for (int i = 0; i < 8; i++) {
+      rowacc[i] = (MODE == MODE_NNMIN) ? __longlong_as_double(0x7ff0000000000000LL) : 0.0;
+      rowidx[i] = -1;
+    }
     mbar_wait(&bar_x, px);
     px ^= 1;
 
@@ -344,6 +350,12 @@ cov_tile_kernel(const double* __restrict__ xp, const double* __restrict__ xnorm,
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int64_t c = col0 + wc0 + tx + 8 * j;
+          if (MODE == MODE_NNMIN) {
+            // running minimum of the squared distance over every point but the cell itself
+            const double sq = (xn[i] - 2.0 * acc[i][j]) + yn[j];
+            if (c < m && c != r + self_offset && sq < rowacc[i]) { rowacc[i] = sq; rowidx[i] = c; }
+            continue;
+          }
           double v = eval_leaf<KIND>(acc[i][j], xn[i], yn[j], par.c1, par.alpha);
           if (MODE == MODE_STORE) {
             if (r < n && c < m) out[r * ldo + c] = v;
@@ -355,6 +367,29 @@ cov_tile_kernel(const double* __restrict__ xp, const double* __restrict__ xnorm,
       __syncthreads();  // everyone is done with ys[buf] (and xs on the last tile)
     }
 
+    if (MODE == MODE_NNMIN) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        double s = rowacc[i];
+        int64_t id = rowidx[i];
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          double s2 = __shfl_xor_sync(0xffffffffu, s, o);
+          int64_t id2 = __shfl_xor_sync(0xffffffffu, id, o);
+          if (s2 < s || (s2 == s && id2 >= 0 && (id < 0 || id2 < id))) { s = s2; id = id2; }
+        }
+        if (tx == 0) { mv_red[warp & 1][wr0 + ty + 4 * i] = s; nn_red[warp & 1][wr0 + ty + 4 * i] = id; }
+      }
+      __syncthreads();
+      if (tid < BM) {
+        int64_t r = row0 + tid;
+        double s = mv_red[0][tid], s2 = mv_red[1][tid];
+        int64_t id = nn_red[0][tid], id2 = nn_red[1][tid];
+        if (s2 < s || (s2 == s && id2 >= 0 && (id < 0 || id2 < id))) { s = s2; id = id2; }
+        if (r < n) { out[r * ldo] = s; nn_idx[r] = id; }
+      }
+      __syncthreads();
+    }
     if (MODE == MODE_MATVEC) {
 #pragma unroll
       for (int i = 0; i < 8; i++) {
@@ -371,6 +406,25 @@ cov_tile_kernel(const double* __restrict__ xp, const double* __restrict__ xnorm,
       }
       __syncthreads();
     }
+  }
+}
+
+// exact Euclidean distance of each row to its selected neighbour: sqrt(sum (x_i - y_j)^2), one warp per row
+__global__ void nn_exact_kernel(const double* __restrict__ x, int64_t n, const double* __restrict__ y, int d,
+                                const int64_t* __restrict__ idx, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int64_t j = idx[i];
+    double s = 0.0;
+    if (j >= 0)
+      for (int c = lane; c < d; c += 32) {
+        double t = x[i * d + c] - y[j * d + c];
+        s = fma(t, t, s);
+      }
+    s = warp_sum(s);
+    if (lane == 0) out[i] = (j >= 0) ? sqrt(s) : __longlong_as_double(0x7ff8000000000000LL);
   }
 }
 
@@ -501,6 +555,8 @@ int ldp_for(int d) {
 }
 
 struct Plan {
+  bool same = false;  // y is x (symmetric landmark covariance)
+  double in_cols = 0.0;  // columns of the input matrices
   Program prog;
   DevProgram dprog;
   std::vector<Operand> xo, yo;
@@ -514,6 +570,8 @@ int prepare(mb_ctx* ctx, const mb_kprog* kp, const mb_mat* x, const mb_mat* y, P
   MB_TRY(parse_program(kp, x->cols, &plan->prog));
   to_dev_program(plan->prog, &plan->dprog);
   const bool same = (x->p == y->p && x->rows == y->rows);
+  plan->same = same;
+  plan->in_cols = (double)x->cols;
   const int nl = (int)plan->prog.leaves.size();
   size_t total = 0;
   std::vector<size_t> off_xp(nl), off_xn(nl), off_yp(nl), off_yn(nl), off_dims(nl);
@@ -571,6 +629,20 @@ int prepare(mb_ctx* ctx, const mb_kprog* kp, const mb_mat* x, const mb_mat* y, P
   return 0;
 }
 
+// stopwatch class of a launch + its algorithmic HBM bytes: inputs once, output once
+template <int MODE>
+int prof_class(mb_ctx* ctx, const Plan& plan, int64_t n, int64_t m) {
+  const int cls = (MODE == MODE_MATVEC) ? MB_PROF_MATVEC : (plan.same ? MB_PROF_OTHER : MB_PROF_COV);
+  if (ctx->prof_on) {
+    double d = 0.0;
+    for (const Leaf& l : plan.prog.leaves) d = std::max<double>(d, l.all_dims ? 0.0 : (double)l.dims.size());
+    double bytes = (MODE == MODE_MATVEC) ? 8.0 * ((double)n + (double)m) : 8.0 * (double)n * (double)m;
+    ctx->prof_work[cls] += bytes + 8.0 * plan.in_cols * ((double)n + (plan.same ? 0.0 : (double)m));
+    (void)d;
+  }
+  return cls;
+}
+
 template <int MODE>
 int launch_fast(mb_ctx* ctx, const Plan& plan, int64_t n, int64_t m, double* out, int64_t ldo, const double* w,
                 double mu, bool* done) {
@@ -585,6 +657,7 @@ int launch_fast(mb_ctx* ctx, const Plan& plan, int64_t n, int64_t m, double* out
   LeafParams par = plan.dprog.leaf[0];
   int64_t n_panels = ceil_div64(n, BM);
   int grid = (int)min(n_panels, (int64_t)ctx->n_sm);
+  const int prof_cls = prof_class<MODE>(ctx, plan, n, m);
 #define MB_COV_CASE(K)                                                                                        \
   case K: {                                                                                                   \
     static bool cfg = false;                                                                                  \
@@ -593,7 +666,7 @@ int launch_fast(mb_ctx* ctx, const Plan& plan, int64_t n, int64_t m, double* out
                                    200 * 1024));                                                              \
       cfg = true;                                                                                             \
     }                                                                                                         \
-    MB_LAUNCH(ctx, (cov_tile_kernel<K, MODE>), grid, NT, smem, xo.p, xo.norm, n, yo.p, yo.norm, m, ldp, par,  \
+    MB_LAUNCH_P(ctx, prof_cls, (cov_tile_kernel<K, MODE>), grid, NT, smem, xo.p, xo.norm, n, yo.p, yo.norm, m, ldp, par,  \
               out, ldo, w, mu);                                                                               \
     break;                                                                                                    \
   }
@@ -625,7 +698,8 @@ int launch_general(mb_ctx* ctx, const Plan& plan, int64_t n, int64_t m, double* 
     G.ldp[l] = plan.xo[l].ldp;
   }
   int grid = (int)min(ceil_div64(n, 64), (int64_t)ctx->n_sm * 4);
-  MB_LAUNCH(ctx, cov_general_kernel<MODE>, grid, 256, 0, plan.dprog, G, n, m, out, ldo, w, mu);
+  const int prof_cls = prof_class<MODE>(ctx, plan, n, m);
+  MB_LAUNCH_P(ctx, prof_cls, cov_general_kernel<MODE>, grid, 256, 0, plan.dprog, G, n, m, out, ldo, w, mu);
   return 0;
 }
 
@@ -764,6 +838,61 @@ extern "C" int mb_predict_mean(mb_ctx* ctx, const mb_kprog* prog, const double* 
     cudaEventDestroy(up[b]);
     cudaEventDestroy(done[b]);
   }
+  return rc;
+}
+
+extern "C" int mb_nn_distances(mb_ctx* ctx, const mb_mat* x, const mb_mat* all, int64_t self_offset, mb_mat* dist,
+                               int64_t* idx_host) {
+  MB_CHECK(ctx && x && all && dist, "mb_nn_distances: null argument");
+  MB_CHECK(x->cols == all->cols, "mb_nn_distances: feature counts differ (%lld vs %lld)", (long long)x->cols,
+           (long long)all->cols);
+  MB_CHECK(dist->rows * dist->cols == x->rows, "mb_nn_distances: output has %lld entries for %lld rows",
+           (long long)(dist->rows * dist->cols), (long long)x->rows);
+  MB_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = x->rows, m = all->rows;
+  if (n == 0) return 0;
+  mb_kop op = {MB_OP_LEAF, MB_K_DISTANCE, 1.0, 1.0, 0.0, 0, -1};
+  mb_kprog prog = {1, 0, &op, nullptr};
+  int64_t* idx_dev = nullptr;
+  MB_CUDA(cudaMalloc(&idx_dev, sizeof(int64_t) * n));
+  int rc = 0;
+  {
+    Plan plan;
+    rc = prepare(ctx, &prog, x, all, &plan);
+    bool done = false;
+    if (rc == 0) {
+      const Operand& xo = plan.xo[0];
+      const Operand& yo = plan.yo[0];
+      size_t smem = (size_t)(BM + 2 * BN) * xo.ldp * sizeof(double);
+      if (smem > 200 * 1024) {
+        mb_set_error("mb_nn_distances: %lld features are too many for the tile kernel", (long long)x->cols);
+        rc = -2;
+      } else {
+        static bool cfg = false;
+        if (!cfg) {
+          cudaFuncSetAttribute(cov_tile_kernel<MB_K_DISTANCE, MODE_NNMIN>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          cfg = true;
+        }
+        int grid = (int)min(ceil_div64(n, BM), (int64_t)ctx->n_sm);
+        cov_tile_kernel<MB_K_DISTANCE, MODE_NNMIN><<<grid, NT, smem, ctx->stream>>>(
+            xo.p, xo.norm, n, yo.p, yo.norm, m, xo.ldp, plan.dprog.leaf[0], dist->p, 1, nullptr, 0.0, self_offset,
+            idx_dev);
+        ctx->launches++;
+        done = cudaGetLastError() == cudaSuccess;
+        if (!done) { mb_set_error("mb_nn_distances: launch failed"); rc = -1; }
+      }
+    }
+    if (rc == 0) {
+      int grid = (int)min((int64_t)ctx->n_sm * 8, ceil_div64(n, 8));
+      nn_exact_kernel<<<grid, 256, 0, ctx->stream>>>(x->p, n, all->p, (int)x->cols, idx_dev, dist->p);
+      ctx->launches++;
+      if (idx_host) cudaMemcpyAsync(idx_host, idx_dev, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+  }
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(idx_dev);
+  if (rc == 0 && cudaGetLastError() != cudaSuccess) { mb_set_error("mb_nn_distances: kernel failed"); rc = -1; }
   return rc;
 }
 

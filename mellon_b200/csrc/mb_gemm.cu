@@ -297,7 +297,8 @@ int launch_gemm(mb_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, cons
   int grid = (int)min(nt, (int64_t)ctx->n_sm);
   int a_vec = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
   int b_vec = ((ldb & 1) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
-  MB_LAUNCH(ctx, (gemm_dmma_kernel<AK, BK>), grid, NTHREADS, SMEM_BYTES, m, n, k, alpha, A, lda, B, ldb, beta,
+  if (ctx->prof_on) ctx->prof_work[MB_PROF_GEMM] += (lower_only ? 1.0 : 2.0) * (double)m * (double)n * (double)k;
+  MB_LAUNCH_P(ctx, MB_PROF_GEMM, (gemm_dmma_kernel<AK, BK>), grid, NTHREADS, SMEM_BYTES, m, n, k, alpha, A, lda, B, ldb, beta,
             C, ldc, lower_only ? 1 : 0, tn, nt, a_vec, b_vec);
   return 0;
 }

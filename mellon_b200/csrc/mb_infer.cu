@@ -287,7 +287,8 @@ int launch_fused(mb_ctx* ctx, const mb_mat* L, const double* zdev, double mu, co
   {                                                                                                       \
     rows_per_cta = ceil_div64(rows_per_cta, RGV) * RGV;                                                   \
     int grid = (int)ceil_div64(n, rows_per_cta);                                                          \
-    MB_LAUNCH(ctx, (fused_rows_kernel<CPV, RGV, SQ>), grid, 512, 0, L->p, n, r, zdev, mu, V, rows_per_cta, \
+    if (ctx->prof_on) ctx->prof_work[MB_PROF_LOSSGRAD] += 8.0 * ((double)n * r + (double)n);                \
+    MB_LAUNCH_P(ctx, MB_PROF_LOSSGRAD, (fused_rows_kernel<CPV, RGV, SQ>), grid, 512, 0, L->p, n, r, zdev, mu, V, rows_per_cta, \
               pb->partial, pb->lpartial);                                                                 \
     MB_LAUNCH(ctx, reduce_chunks_kernel, (int)ceil_div64(r + 1, 256), 256, 0, pb->partial, grid, r,       \
               pb->lpartial, SQ ? 0 : grid, pb->out);                                                      \

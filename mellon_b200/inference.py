@@ -35,6 +35,8 @@ DEFAULT_INIT_LEARN_RATE = 1e-1
 DEFAULT_NUM_SAMPLES = 40
 DEFAULT_OPTIMIZER = "L-BFGS-B"
 DEFAULT_JIT = False
+# what jaxopt.ScipyMinimize(method="L-BFGS-B") hands to scipy.optimize.minimize (maxiter=500, tol=None)
+LBFGSB_OPTIONS = {"maxiter": 500}
 
 
 class Transform:
@@ -136,7 +138,7 @@ def minimize_lbfgsb(loss_func, initial_value, jit=DEFAULT_JIT):
     here so the trajectory is the reference's up to the rounding of (loss, grad)."""
     fun = _value_and_grad(loss_func)
     res = minimize(fun, np.asarray(initial_value, dtype=np.float64), jac=True, tol=None, method="L-BFGS-B",
-                   options={"maxiter": 500})
+                   options=dict(LBFGSB_OPTIONS))
     state = ScipyMinimizeInfo(
         fun_val=np.asarray(res.fun),
         success=res.success,

@@ -1,0 +1,6 @@
+"""Estimator classes (``mellon/model.py``)."""
+
+from .density_estimator import DensityEstimator
+from .time_sensitive_density_estimator import TimeSensitiveDensityEstimator
+
+__all__ = ["DensityEstimator", "TimeSensitiveDensityEstimator"]

@@ -541,12 +541,12 @@ ScipyMinimizeInfo = namedtuple(
 Results = namedtuple("Results", "pre_transformation opt_state loss")
 
 
-def minimize_lbfgsb(value_and_grad, initial_value):
+def minimize_lbfgsb(value_and_grad, initial_value, options=None):
     """inference.py:272-288 via jaxopt.ScipyMinimize(method="L-BFGS-B") defaults:
     scipy.optimize.minimize(fun, x0, jac=True, tol=None, method="L-BFGS-B",
     options={"maxiter": 500})."""
     res = minimize(value_and_grad, np.asarray(initial_value, dtype=np.float64), jac=True,
-                   tol=None, method="L-BFGS-B", options={"maxiter": 500})
+                   tol=None, method="L-BFGS-B", options=options or {"maxiter": 500})
     state = ScipyMinimizeInfo(res.fun, res.success, res.status, res.nit,
                               getattr(res, "hess_inv", None), res.nfev,
                               getattr(res, "njev", res.nfev), 0)
@@ -661,7 +661,8 @@ FitResult = namedtuple(
 def fit_density(x, cov_func_curry=Matern52, n_landmarks=None, rank=None, gp_type=None,
                 jitter=DEFAULT_JITTER, landmarks=None, nn_distances=None, d=None, mu=None,
                 ls=None, ls_factor=1, cov_func=None, Lp=None, L=None, initial_value=None,
-                random_state=DEFAULT_RANDOM_SEED, timings=None):
+                random_state=DEFAULT_RANDOM_SEED, timings=None, lbfgsb_options=None,
+                grad_noise=0.0):
     """density_estimator.py:404-444, 494-516, 542-581 + base_model.py:371-431 with the
     default L-BFGS-B optimiser.  `timings`, when a dict, receives per-stage seconds."""
     import time
@@ -701,7 +702,18 @@ def fit_density(x, cov_func_curry=Matern52, n_landmarks=None, rank=None, gp_type
         initial_value = compute_initial_value(nn_distances, d, mu, L)
     t3 = tick()
     k = initial_value.shape[0]
-    res = minimize_lbfgsb(lambda z: loss_and_grad(L, nn_distances, d, mu, z, k), initial_value)
+    if grad_noise:
+        # reference-vs-reference noise floor: perturb (loss, grad) at rounding level
+        noise_rng = np.random.default_rng(12345)
+
+        def vg(z):
+            l, g = loss_and_grad(L, nn_distances, d, mu, z, k)
+            return l * (1 + grad_noise * noise_rng.standard_normal()), \
+                g * (1 + grad_noise * noise_rng.standard_normal(g.shape))
+    else:
+        def vg(z):
+            return loss_and_grad(L, nn_distances, d, mu, z, k)
+    res = minimize_lbfgsb(vg, initial_value, options=lbfgsb_options)
     t4 = tick()
     log_density_x = np.asarray(L).dot(res.pre_transformation) + mu
     t5 = tick()

@@ -1,0 +1,271 @@
+"""GPU parity, end to end: the drop-in estimators against the CPU oracle's restatement of the
+reference pipeline on identical inputs (identical nn_distances / landmarks, so neighbour and
+landmark index selection is an input identity).  Tolerance of north_star: log-density within
+1e-5 relative."""
+
+import numpy as np
+import pytest
+
+import mellon_b200 as mb
+from mellon_b200 import cov as C
+from oracle import mellon_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5          # north_star: log-density within 1e-5 relative
+TIGHT_TOL = 1e-6    # both optimisers run to convergence: same optimum
+TIGHT = dict(maxiter=20000, maxfun=100000, ftol=0.0, gtol=1e-9)
+
+
+@pytest.fixture
+def tight():
+    """Run L-BFGS-B to convergence on both sides.
+
+    With SciPy's default stop (ftol 2.2e-9, what jaxopt.ScipyMinimize uses) the result on
+    CLUSTERED data sits ~4e-5 (relative log density) away from the converged optimum, and
+    rounding-level noise in (loss, grad) — a different BLAS thread count is enough — moves it by
+    ~1e-5: the reference-vs-reference noise floor (SURVEY.md §7 hard part 1, measured again in
+    `test_default_stop_is_within_the_noise_floor`).  Parity of the OBJECTIVE is therefore shown at
+    convergence, where that floor is ~3e-8; parity at the default stop is shown on the BASELINE
+    synthetic inputs (uniform cells), where the optimisation is benign."""
+    old = dict(mb.inference.LBFGSB_OPTIONS)
+    mb.inference.LBFGSB_OPTIONS.clear()
+    mb.inference.LBFGSB_OPTIONS.update(TIGHT)
+    yield TIGHT
+    mb.inference.LBFGSB_OPTIONS.clear()
+    mb.inference.LBFGSB_OPTIONS.update(old)
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b) / np.abs(b)))
+
+
+def blobs(n, d, seed, k=6, spread=0.25):
+    """Clustered cells; the cluster centres depend on d only, so differently seeded draws (training
+    cells, query cells) come from the same distribution."""
+    centers = np.random.default_rng(1000 + d).standard_normal((k, d)) * 1.5
+    rng = np.random.default_rng(seed)
+    return centers[rng.integers(0, k, n)] + spread * rng.standard_normal((n, d))
+
+
+def test_config1_readme_smoke_full_gp(be):
+    """BASELINE configs[0]: DensityEstimator().fit_predict(rand(100, 10)), default Matern52 -> FULL GP."""
+    X = np.random.default_rng(0).random((100, 10))
+    est = mb.DensityEstimator()
+    dens = est.fit_predict(X)
+    ref = O.fit_density(X)
+    assert est.gp_type == mb.util.GaussianProcessType.FULL and est.landmarks is None
+    assert dens.shape == (100,)
+    assert est.mu == pytest.approx(ref.mu, rel=1e-14) and est.ls == pytest.approx(ref.ls, rel=1e-14)
+    assert rel(dens, ref.log_density_x) < TOL
+    # predict(X) reproduces fit_predict(X) (tests/test_density_estimator.py:30-44)
+    # jitter makes the interpolation inexact: K (K + 1e-6 I)^-1 f != f; same deviation on both sides
+    pred = est.predict(X)
+    assert rel(pred, O.predict_density(ref, X, X)) < TOL
+    assert np.std(pred - dens) / np.std(dens) < 1e-3
+    Y = np.random.default_rng(1).random((100, 10))
+    assert rel(est.predict(Y), O.predict_density(ref, X, Y)) < TOL
+    assert isinstance(est.predict, mb.conditional.FullConditional)
+
+
+@pytest.mark.parametrize("cov_o,cov_c", [(O.Matern52, C.Matern52), (O.ExpQuad, C.ExpQuad), (O.Matern32, C.Matern32)])
+def test_sparse_cholesky_matches_oracle(be, tight, cov_o, cov_c):
+    X = blobs(3000, 8, 1)
+    nn = O.compute_nn_distances(X)
+    lm = X[np.random.default_rng(2).choice(3000, 200, replace=False)].copy()
+    ref = O.fit_density(X, cov_func_curry=cov_o, landmarks=lm, nn_distances=nn, lbfgsb_options=tight)
+    est = mb.DensityEstimator(cov_func_curry=cov_c, landmarks=lm, nn_distances=nn, check_rank=False)
+    dens = est.fit_predict(X)
+    assert est.gp_type == mb.util.GaussianProcessType.SPARSE_CHOLESKY
+    # stage-wise at fixed inputs
+    Lp, L = np.asarray(est.Lp), np.asarray(est.L)
+    assert np.max(np.abs(Lp @ Lp.T - ref.Lp @ ref.Lp.T)) < 1e-12
+    assert np.max(np.abs(L @ L.T - ref.L @ ref.L.T)) < 1e-6
+    # the objective at a fixed point: loss / gradient / transform against the oracle's own L
+    z = ref.pre_transformation
+    loss, grad = est.loss_func.value_and_grad(z)
+    lref, gref = O.loss_and_grad(ref.L, nn, ref.d, ref.mu, z)
+    assert abs(loss - lref) < 1e-9 * abs(lref)
+    assert np.max(np.abs(grad - gref)) < 1e-6 * np.max(np.abs(gref)) + 1e-7
+    assert rel(est.transform(z), ref.log_density_x) < 1e-8
+    assert rel(dens, ref.log_density_x) < TIGHT_TOL
+    Y = blobs(500, 8, 3)
+    assert rel(est.predict(Y), O.predict_density(ref, X, Y)) < TIGHT_TOL
+    assert isinstance(est.predict, mb.conditional.LandmarksConditionalCholesky)
+
+
+def test_default_stop_is_within_the_noise_floor(be):
+    """Default L-BFGS-B stop on clustered data: the GPU result is as close to the oracle's as the
+    oracle is to itself under 1e-15 relative noise in (loss, grad), and both are equally far from
+    the converged optimum."""
+    X = blobs(3000, 8, 1)
+    nn = O.compute_nn_distances(X)
+    lm = X[np.random.default_rng(2).choice(3000, 200, replace=False)].copy()
+    ref = O.fit_density(X, landmarks=lm, nn_distances=nn)
+    noisy = O.fit_density(X, landmarks=lm, nn_distances=nn, grad_noise=1e-15)
+    best = O.fit_density(X, landmarks=lm, nn_distances=nn, lbfgsb_options=TIGHT)
+    floor = rel(noisy.log_density_x, ref.log_density_x)
+    stop = rel(ref.log_density_x, best.log_density_x)
+    dens = mb.DensityEstimator(landmarks=lm, nn_distances=nn, check_rank=False).fit_predict(X)
+    assert rel(dens, ref.log_density_x) < 10 * max(floor, stop)
+    assert rel(dens, best.log_density_x) < 3 * stop + 1e-6
+
+
+def test_uniform_data_large_length_scale(be):
+    """The BASELINE synthetic shape (uniform cells => ls >> extent, K_MM + 1e-6 I nearly singular)."""
+    X = np.random.default_rng(0).random((4000, 50))
+    nn = O.compute_nn_distances(X)
+    lm = X[:300].copy()
+    ref = O.fit_density(X, cov_func_curry=O.ExpQuad, landmarks=lm, nn_distances=nn)
+    est = mb.DensityEstimator(cov_func_curry=C.ExpQuad, landmarks=lm, nn_distances=nn, check_rank=False)
+    dens = est.fit_predict(X)
+    assert rel(dens, ref.log_density_x) < TOL
+
+
+@pytest.mark.parametrize("rank", [40, 0.99])
+def test_sparse_nystroem_matches_oracle(be, tight, rank):
+    X = blobs(2500, 6, 5)
+    nn = O.compute_nn_distances(X)
+    lm = X[np.random.default_rng(6).choice(2500, 150, replace=False)].copy()
+    ref = O.fit_density(X, landmarks=lm, nn_distances=nn, rank=rank, lbfgsb_options=tight)
+    est = mb.DensityEstimator(landmarks=lm, nn_distances=nn, rank=rank)
+    dens = est.fit_predict(X)
+    assert est.gp_type == mb.util.GaussianProcessType.SPARSE_NYSTROEM
+    # integer rank selection is bit-exact
+    assert est.L.shape == ref.L.shape
+    L = np.asarray(est.L)
+    assert np.max(np.abs(L @ L.T - ref.L @ ref.L.T)) < 1e-6
+    assert rel(dens, ref.log_density_x) < TIGHT_TOL
+    Y = blobs(300, 6, 7)
+    assert rel(est.predict(Y), O.predict_density(ref, X, Y)) < 10 * TIGHT_TOL
+    assert isinstance(est.predict, mb.conditional.LandmarksConditional)
+
+
+def test_full_nystroem(be, tight):
+    X = blobs(300, 4, 8)
+    nn = O.compute_nn_distances(X)
+    ref = O.fit_density(X, nn_distances=nn, rank=0.95, gp_type=O.GaussianProcessType.FULL_NYSTROEM, n_landmarks=0,
+                        lbfgsb_options=tight)
+    est = mb.DensityEstimator(nn_distances=nn, rank=0.95, gp_type="full_nystroem", n_landmarks=0)
+    dens = est.fit_predict(X)
+    assert est.L.shape == ref.L.shape
+    assert rel(dens, ref.log_density_x) < TOL
+
+
+def test_one_dimensional_input_and_default_pipeline(be, tight):
+    x = np.random.default_rng(3).standard_normal(400)
+    est = mb.DensityEstimator()
+    dens = est.fit_predict(x)
+    ref = O.fit_density(x.reshape(-1, 1), lbfgsb_options=tight)
+    assert dens.shape == (400,)
+    assert rel(dens, ref.log_density_x) < TOL
+
+
+def test_default_landmarks_kmeans_identical_on_both_sides(be, tight):
+    """With landmarks=None both sides call sklearn k_means(n_init=1, random_state=42)."""
+    X = blobs(1200, 5, 12)
+    est = mb.DensityEstimator(n_landmarks=60)
+    dens = est.fit_predict(X)
+    ref = O.fit_density(X, n_landmarks=60, lbfgsb_options=tight)
+    # sklearn's threaded Lloyd iterations sum per-thread partial centroids in a non-deterministic
+    # order: centroids agree to rounding, the cluster ASSIGNMENT (index selection) is bit-exact
+    lm = np.asarray(est.landmarks)
+    np.testing.assert_allclose(lm, ref.landmarks, rtol=1e-12, atol=1e-12)
+    assign = lambda c: np.argmin(((X[:, None, :] - c[None]) ** 2).sum(-1), axis=1)
+    assert np.array_equal(assign(lm), assign(ref.landmarks))
+    assert np.array_equal(np.asarray(est.nn_distances), ref.nn_distances)  # bit-exact neighbour selection
+    ref = O.fit_density(X, landmarks=lm, nn_distances=ref.nn_distances, lbfgsb_options=tight)
+    assert rel(dens, ref.log_density_x) < TIGHT_TOL
+
+
+def test_laplace_uncertainty(be):
+    X = blobs(1500, 5, 13)
+    nn = O.compute_nn_distances(X)
+    lm = X[:100].copy()
+    est = mb.DensityEstimator(landmarks=lm, nn_distances=nn, predictor_with_uncertainty=True, check_rank=False)
+    est.fit(X)
+    ref = O.fit_density(X, landmarks=lm, nn_distances=nn)
+    std_ref = O.laplace_std_from_diag(O.hessian_diag(ref.L, nn, ref.d, ref.mu, ref.pre_transformation))
+    np.testing.assert_allclose(est.pre_transformation_std, std_ref, rtol=1e-4)
+    Y = blobs(200, 5, 14)
+    pred = est.predict
+    unc = pred.uncertainty(Y)
+    np.testing.assert_allclose(unc, pred.covariance(Y) + pred.mean_covariance(Y), rtol=1e-12)
+    # oracle for the two terms (conditional.py:930-963)
+    from scipy.linalg import solve_triangular
+
+    Kus = ref.cov_func(lm, Y)
+    A = solve_triangular(ref.Lp, Kus, lower=True)
+    var = ref.cov_func.diag(Y) - np.sum(A * A, axis=0)
+    W = solve_triangular(ref.Lp.T, np.diag(std_ref))
+    mvar = np.sum((ref.cov_func(Y, lm) @ W) ** 2, axis=1)
+    np.testing.assert_allclose(pred.covariance(Y), var, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(pred.mean_covariance(Y), mvar, rtol=1e-4)
+
+
+def test_time_sensitive_estimator(be, tight):
+    rng = np.random.default_rng(21)
+    n_per, T, d = 300, 4, 3
+    X = np.concatenate([blobs(n_per, d, 30 + t) + 0.2 * t for t in range(T)])
+    times = np.repeat(np.arange(T, dtype=float), n_per)
+    lm_idx = rng.choice(n_per * T, 120, replace=False)
+    Xt = np.concatenate([X, times[:, None]], axis=1)
+    lm = Xt[lm_idx].copy()
+    est = mb.TimeSensitiveDensityEstimator(ls=1.5, ls_time=0.8, landmarks=lm, check_rank=False)
+    dens = est.fit_predict(X, times)
+    # oracle: same pipeline with per-time-point nn distances and the product kernel
+    nn = np.empty(n_per * T)
+    for t in range(T):
+        mask = times == t
+        nn[mask] = O.compute_nn_distances(X[mask])
+    np.testing.assert_array_equal(est.nn_distances, nn)
+    cov = O.Matern52(1.5, active_dims=slice(None, -1)) * O.Matern52(0.8, active_dims=-1)
+    ref = O.fit_density(Xt, cov_func=cov, landmarks=lm, nn_distances=nn, d=d, ls=1.5, lbfgsb_options=tight)
+    assert rel(dens, ref.log_density_x) < TOL
+    pred = est.predict
+    assert isinstance(pred, mb.conditional.LandmarksConditionalCholeskyTime)
+    out = pred(X[:50], times[:50])
+    assert rel(out, O.predict_density(ref, Xt, Xt[:50])) < TOL
+    # scalar time is broadcast, multi_time stacks on axis 1
+    at1 = pred(X[:50], 1.0)
+    mt = pred(X[:50], multi_time=[1.0, 2.0])
+    assert mt.shape == (50, 2) and np.allclose(mt[:, 0], at1, rtol=1e-13)
+
+
+def test_error_contracts(be):
+    X = np.random.default_rng(0).random((60, 3))
+    est = mb.DensityEstimator()
+    est.fit(X)
+    with pytest.raises(ValueError):
+        est.predict(np.zeros((5, 4)))            # wrong feature count
+    with pytest.raises(ValueError):
+        est.fit_predict(X.copy())                 # a different x object
+    with pytest.raises(ValueError):
+        est.predict.covariance(X)                 # built without uncertainty
+    with pytest.raises(ValueError):
+        mb.DensityEstimator().fit_predict()       # no x
+    with pytest.raises(ValueError):
+        mb.DensityEstimator().fit_predict(np.random.default_rng(0).random((30, 51)))  # d > 50
+    # non positive definite covariance -> the reference's ValueError text
+    x = np.arange(10.0).reshape(5, 2) + 1.0
+    with pytest.raises(ValueError, match="not positively definite"):
+        mb.parameters.compute_Lp(x, C.Linear(1.0) * -1.0, gp_type="full", jitter=1e-12)
+    # normalize
+    p = est.predict
+    assert np.allclose(p(X, normalize=True), p(X) - np.log(60))
+
+
+def test_predictor_json_roundtrip(be, tmp_path):
+    X = blobs(500, 4, 40)
+    est = mb.DensityEstimator(n_landmarks=40)
+    est.fit(X)
+    p = est.predict
+    q = mb.Predictor.from_json_str(p.to_json())
+    assert np.allclose(q(X[:20]), p(X[:20]), rtol=1e-12)
+    for comp in (None, "gzip", "bz2"):
+        f = str(tmp_path / "pred.json")
+        p.to_json(f, compress=comp)
+        name = f + {None: "", "gzip": ".gz", "bz2": ".bz2"}[comp]
+        q = mb.Predictor.from_json(name)
+        assert np.allclose(q(X[:20]), p(X[:20]), rtol=1e-12)

@@ -1,0 +1,277 @@
+"""GPU parity, kernel by kernel: every C-ABI entry point against the CPU oracle on the same
+seeded inputs (float64; tolerances stated per test, relative to the magnitude of the result)."""
+
+import numpy as np
+import pytest
+from scipy.linalg import solve_triangular
+
+import mellon_b200 as mb
+from mellon_b200 import cov as C
+from oracle import mellon_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b))))
+
+
+PAIRS = [
+    (C.Matern32, O.Matern32), (C.Matern52, O.Matern52), (C.ExpQuad, O.ExpQuad),
+    (C.Exponential, O.Exponential), (C.Linear, O.Linear),
+]
+
+
+@pytest.mark.parametrize("n,m,d", [(1, 1, 1), (7, 5, 3), (129, 65, 10), (300, 257, 50), (64, 128, 51),
+                                   (1000, 333, 2), (130, 70, 200)])
+@pytest.mark.parametrize("pair", PAIRS, ids=lambda p: p[0].__name__)
+def test_cov_build_matches_oracle(be, pair, n, m, d):
+    rng = np.random.default_rng(n * 1000 + m + d)
+    x, y = rng.random((n, d)), rng.random((m, d))
+    ls = 0.7 * np.sqrt(d)
+    K = np.asarray(pair[0](ls)(x, y))
+    Kref = pair[1](ls)(x, y)
+    assert K.shape == (n, m)
+    np.testing.assert_allclose(K, Kref, rtol=0, atol=2e-13 * max(1.0, np.abs(Kref).max()))
+
+
+def test_ratquad_and_alpha_first_positional(be):
+    rng = np.random.default_rng(3)
+    x, y = rng.random((50, 6)), rng.random((41, 6))
+    K = np.asarray(C.RatQuad(2.5, 1.3)(x, y))
+    np.testing.assert_allclose(K, O.RatQuad(2.5, 1.3)(x, y), rtol=0, atol=1e-13)
+
+
+def test_distance_semantics(be):
+    """+1e-12 inside the sqrt: d(x, x) == 1e-6 exactly-ish, and the diag of a kernel is not 1."""
+    x = np.random.default_rng(0).random((20, 4))
+    D = np.asarray(mb.util.distance(x, x))
+    # compare SQUARED distances: on the diagonal sq = 1e-12 + (cancellation residue of xx - 2xy + yy),
+    # and that residue (a few ulp of xx) depends on the summation order of the dot products
+    np.testing.assert_allclose(D * D, O.distance(x, x) ** 2, rtol=0, atol=16 * np.finfo(float).eps * 4)
+    assert np.allclose(np.diag(D), 1e-6, rtol=1e-3)
+    dg = C.Matern52(1.0).diag(x)
+    np.testing.assert_allclose(dg, O.Matern52(1.0).diag(x), rtol=0, atol=1e-15)
+    assert np.all(dg < 1.0)
+
+
+ACTIVE = [None, 2, -1, slice(1, 4), [0, 3], [True, False, True, False, True]]
+
+
+@pytest.mark.parametrize("ad", ACTIVE, ids=str)
+def test_active_dims(be, ad):
+    rng = np.random.default_rng(11)
+    x, y = rng.random((33, 5)), rng.random((34, 5))
+    K = np.asarray(C.Matern32(0.9, active_dims=ad)(x, y))
+    np.testing.assert_allclose(K, O.Matern32(0.9, active_dims=ad)(x, y), rtol=0, atol=1e-13)
+
+
+def test_algebra_hierarchy(be):
+    """Add / Mul / Pow with scalars and nested active_dims (tests/test_base_cov.py:120-160 shape)."""
+    rng = np.random.default_rng(5)
+    x, y = rng.random((40, 6)), rng.random((37, 6))
+    k = (C.Matern52(1.2, active_dims=slice(None, -1)) * C.ExpQuad(0.4, active_dims=-1) + 0.3) ** 2
+    ko = (O.Matern52(1.2, active_dims=slice(None, -1)) * O.ExpQuad(0.4, active_dims=-1) + 0.3) ** 2
+    np.testing.assert_allclose(np.asarray(k(x, y)), ko(x, y), rtol=1e-13, atol=1e-13)
+    k2 = 0.2 + C.Linear(2.0, active_dims=[0, 1]) * 1.5 + C.Exponential(0.8) * C.RatQuad(1.5, 0.9, active_dims=[2, 4])
+    k2o = 0.2 + O.Linear(2.0, active_dims=[0, 1]) * 1.5 + O.Exponential(0.8) * O.RatQuad(1.5, 0.9, active_dims=[2, 4])
+    np.testing.assert_allclose(np.asarray(k2(x, y)), k2o(x, y), rtol=1e-13, atol=1e-13)
+    # outer active_dims, children index into the already-selected columns (base_cov.py:310-315)
+    k3 = C.Matern32(0.7, active_dims=[0, 2]) + C.ExpQuad(1.1, active_dims=1)
+    k3.active_dims = [1, 3, 5]
+    k3o = O.Matern32(0.7, active_dims=[0, 2]) + O.ExpQuad(1.1, active_dims=1)
+    k3o.active_dims = [1, 3, 5]
+    np.testing.assert_allclose(np.asarray(k3(x, y)), k3o(x, y), rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(k.diag(x), ko.diag(x), rtol=1e-13)
+
+
+def test_empty_inputs(be):
+    x = np.zeros((0, 3))
+    y = np.random.default_rng(0).random((4, 3))
+    assert np.asarray(C.Matern52(1.0)(x, y)).shape == (0, 4)
+    assert np.asarray(C.Matern52(1.0)(y, x)).shape == (4, 0)
+
+
+def _spd(n, seed, cond=1e6):
+    rng = np.random.default_rng(seed)
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    ev = np.geomspace(1.0, 1.0 / cond, n)
+    return (q * ev) @ q.T
+
+
+@pytest.mark.parametrize("n", [1, 5, 32, 33, 100, 257, 1000])
+def test_potrf(be, n):
+    A = _spd(n, n)
+    Ad = be.upload(A.copy())
+    assert be.potrf(Ad) == 0
+    Lc = Ad.numpy()
+    Lref = np.linalg.cholesky(A)
+    assert np.allclose(np.triu(Lc, 1), 0.0)
+    assert rel_err(Lc @ Lc.T, A) < 1e-13
+    assert rel_err(Lc, Lref) < 1e-9
+
+
+def test_potrf_reports_non_positive_definite(be):
+    A = _spd(64, 1)
+    A[40, 40] = -1.0
+    info = be.potrf(be.upload(A))
+    assert 1 <= info <= 41
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (10, 33), (500, 100), (131, 257)])
+def test_trsm_right(be, n, m):
+    rng = np.random.default_rng(n + m)
+    Lp = np.linalg.cholesky(_spd(m, m, 1e4))
+    X = rng.standard_normal((n, m))
+    out = be.trsm_right_lt(be.upload(Lp), be.upload(X.copy())).numpy()
+    ref = solve_triangular(Lp, X.T, lower=True).T
+    assert rel_err(out, ref) < 1e-11
+
+
+@pytest.mark.parametrize("m,nrhs", [(1, 1), (40, 1), (100, 3), (257, 1), (300, 70), (97, 129)])
+@pytest.mark.parametrize("trans", [False, True])
+def test_tri_solve(be, m, nrhs, trans):
+    rng = np.random.default_rng(m * 7 + nrhs)
+    Lp = np.linalg.cholesky(_spd(m, m + 1, 1e4))
+    B = rng.standard_normal((m, nrhs)) if nrhs > 1 else rng.standard_normal(m)
+    out = be.tri_solve(be.upload(Lp), B, trans=trans)
+    ref = solve_triangular(Lp.T if trans else Lp, B, lower=not trans)
+    assert out.shape == ref.shape
+    assert rel_err(out, ref) < 1e-11
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (17, 9, 5), (128, 128, 16), (130, 257, 77), (300, 65, 1000)])
+def test_gemm(be, ta, tb, m, n, k):
+    rng = np.random.default_rng(m + n + k)
+    A = rng.standard_normal((k, m) if ta else (m, k))
+    B = rng.standard_normal((n, k) if tb else (k, n))
+    out = be.gemm(A, B, trans_a=bool(ta), trans_b=bool(tb)).numpy()
+    ref = (A.T if ta else A) @ (B.T if tb else B)
+    assert rel_err(out, ref) < 1e-13
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n,r", [(1, 1), (50, 7), (1000, 64), (777, 130), (3000, 257)])
+def test_gram_and_ridge(be, variant, n, r):
+    rng = np.random.default_rng(n + r)
+    L = rng.standard_normal((n, r)) / np.sqrt(r)
+    t = rng.standard_normal(n)
+    be.set_option("gemm", variant)
+    try:
+        Ld = be.upload(L, sharded=True)
+        G = be.gram(Ld).numpy()
+        assert rel_err(G, L.T @ L) < 1e-13
+        assert np.array_equal(G, G.T)
+        assert rel_err(be.gemv_t(Ld, t), L.T @ t) < 1e-13
+        if r <= n:
+            z0 = be.ridge_init(Ld, t)
+            assert rel_err(z0, O.ridge_normal_equations(L, t)) < 1e-10
+    finally:
+        be.set_option("gemm", 0)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n,r", [(1, 1), (9, 4), (1000, 64), (513, 33), (2000, 1000), (300, 2050), (4000, 5000)])
+def test_loss_grad_hess_transform(be, variant, n, r):
+    rng = np.random.default_rng(n * 3 + r)
+    L = rng.standard_normal((n, r)) / np.sqrt(r)
+    nn = rng.random(n) * 0.5 + 0.05
+    d, mu = 7.0, -3.0
+    z = rng.standard_normal(r) * 0.3
+    V, Vdr = O.nn_constants(nn, d)
+    be.set_option("lossgrad", variant)
+    try:
+        st = be.objective(L, V, float(np.sum(Vdr)), mu, r)
+        loss, grad = be.loss_grad(st, z)
+        lref, gref = O.loss_and_grad(L, nn, d, mu, z, r)
+        assert abs(loss - lref) <= 1e-12 * abs(lref)
+        assert rel_err(grad, gref) < 1e-12
+        assert rel_err(be.hess_diag(st, z), O.hessian_diag(L, nn, d, mu, z)) < 1e-12
+        assert rel_err(be.transform(st.L, z, mu), L @ z + mu) < 1e-13
+        # bit-reproducible run to run
+        loss2, grad2 = be.loss_grad(st, z)
+        assert loss2 == loss and np.array_equal(grad, grad2)
+    finally:
+        be.set_option("lossgrad", 0)
+
+
+def test_loss_with_per_cell_d(be):
+    rng = np.random.default_rng(9)
+    n, r = 400, 50
+    L = rng.standard_normal((n, r)) / np.sqrt(r)
+    nn = rng.random(n) * 0.5 + 0.05
+    dvec = rng.integers(2, 9, n).astype(float)
+    z = rng.standard_normal(r) * 0.2
+    V, Vdr = O.nn_constants(nn, dvec)
+    st = be.objective(L, V, float(np.sum(Vdr)), -2.0, r)
+    loss, grad = be.loss_grad(st, z)
+    lref, gref = O.loss_and_grad(L, nn, dvec, -2.0, z, r)
+    assert abs(loss - lref) <= 1e-12 * abs(lref)
+    assert rel_err(grad, gref) < 1e-12
+
+
+@pytest.mark.parametrize("nq,m,d,p", [(1, 1, 1, 1), (100, 37, 5, 1), (1000, 500, 50, 1), (300000, 64, 10, 1),
+                                      (257, 129, 7, 3)])
+def test_predict_mean(be, nq, m, d, p):
+    rng = np.random.default_rng(nq + m)
+    xq, xu = rng.random((nq, d)), rng.random((m, d))
+    w = rng.standard_normal((m, p)) if p > 1 else rng.standard_normal(m)
+    cov, covo = C.Matern52(0.8 * np.sqrt(d)), O.Matern52(0.8 * np.sqrt(d))
+    out = be.predict_mean(cov, xq, xu, w, 1.5)
+    ref = 1.5 + covo(xq, xu) @ w
+    assert out.shape == ref.shape
+    assert rel_err(out, ref) < 1e-12
+
+
+def test_predict_mean_product_kernel(be):
+    rng = np.random.default_rng(4)
+    xq, xu, w = rng.random((500, 6)), rng.random((90, 6)), rng.standard_normal(90)
+    cov = C.Matern32(1.1, active_dims=slice(None, -1)) * C.ExpQuad(0.5, active_dims=-1)
+    covo = O.Matern32(1.1, active_dims=slice(None, -1)) * O.ExpQuad(0.5, active_dims=-1)
+    assert rel_err(be.predict_mean(cov, xq, xu, w, -0.5), -0.5 + covo(xq, xu) @ w) < 1e-12
+
+
+@pytest.mark.parametrize("n", [1, 10, 200, 513])
+def test_eigh(be, n):
+    A = _spd(n, n + 3, 1e8)
+    w, V = be.eigh(be.upload(A.copy()))
+    V = V.numpy()
+    wref = np.linalg.eigvalsh(A)
+    assert np.max(np.abs(w - wref)) < 1e-13 * wref.max()
+    assert rel_err((V * w) @ V.T, A) < 1e-12
+    assert rel_err(V.T @ V, np.eye(n)) < 1e-12
+
+
+def test_small_matrix_ops(be):
+    rng = np.random.default_rng(2)
+    A = rng.standard_normal((37, 21))
+    Ad = be.upload(A)
+    assert np.array_equal(be.transpose(Ad).numpy(), A.T)
+    assert np.array_equal(be.copy_cols(Ad, 5, 9).numpy(), A[:, 5:14])
+    s = rng.random(21)
+    assert np.allclose(be.scale_cols(be.copy(Ad), s).numpy(), A * s, rtol=1e-15)
+    assert np.allclose(be.scale(be.copy(Ad), 0.25).numpy(), A * 0.25, rtol=0, atol=0)
+    assert rel_err(be.row_sumsq(Ad), np.sum(A * A, axis=1)) < 1e-14
+    assert np.array_equal(be.eye(5).numpy(), np.eye(5))
+
+
+@pytest.mark.parametrize("n,d", [(2, 1), (50, 3), (1000, 10), (3000, 50)])
+def test_nn_distances_match_exact_search(be, n, d):
+    """tests/test_parameters.py:244-268 semantics: exact nearest neighbour; index selection bit-exact."""
+    from sklearn.neighbors import NearestNeighbors
+
+    x = np.random.default_rng(n + d).random((n, d))
+    dist, idx = be.nn_distances(x, return_index=True)
+    rd, ri = NearestNeighbors(n_neighbors=2, algorithm="brute").fit(x).kneighbors(x)
+    assert np.array_equal(idx, ri[:, 1])
+    np.testing.assert_allclose(dist, rd[:, 1], rtol=1e-13)
+
+
+def test_nn_distances_known_answers(be):
+    """The reference's own known-answer cases (tests/test_parameters.py:244-268)."""
+    x = np.array([[0.0, 0.0], [1.0, 1.0], [2.0, 2.0]])
+    np.testing.assert_allclose(be.nn_distances(x), np.sqrt(2.0) * np.ones(3), rtol=1e-15)
+    x = np.array([[1.0, 1.0], [1.0, 1.0], [1.0, 1.0]])
+    np.testing.assert_array_equal(be.nn_distances(x), np.zeros(3))
