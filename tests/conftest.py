@@ -10,8 +10,9 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
+for p in (ROOT, os.path.dirname(os.path.abspath(__file__))):
+    if p not in sys.path:
+        sys.path.insert(0, p)
 
 
 def pytest_configure(config):
@@ -36,10 +37,28 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
-@pytest.fixture(scope="session")
-def be():
-    """The product backend (one B200 through libmellon_b200.so)."""
-    from mellon_b200.backend import get_backend, set_backend
+_cuda_backend = None
 
+
+@pytest.fixture(params=["fake", pytest.param("cuda", marks=pytest.mark.gpu)])
+def be(request):
+    """The backend under test.
+
+    ``cuda`` (marked ``gpu``): the product backend — one B200 through libmellon_b200.so.
+    ``fake``: the NumPy test double of the C ABI (tests/fake_lib.py), which runs the same host
+    logic (estimators, validation, program compilation, ctypes marshalling) on a box without a
+    GPU; the parity assertions then check the double and the host side against the oracle."""
+    global _cuda_backend
+    from mellon_b200.backend import CudaBackend, set_backend
+
+    if request.param == "cuda":
+        if _cuda_backend is None:
+            _cuda_backend = CudaBackend.from_environment()
+        backend = _cuda_backend
+    else:
+        from fake_lib import FakeBackend
+
+        backend = FakeBackend()
+    set_backend(backend)
+    yield backend
     set_backend(None)
-    return get_backend()

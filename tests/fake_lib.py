@@ -1,0 +1,403 @@
+"""TEST DOUBLE of libmellon_b200.so at the C-ABI level (NumPy/SciPy, float64).
+
+It lets the whole host side of the package — estimator pipeline, validation, covariance-program
+compilation, ctypes marshalling, row sharding and gathers — run on a box without a GPU, including
+world_size-2 runs over `gloo`.  It lives under tests/ and is installed with
+``mellon_b200.set_backend(FakeBackend())``; the product never imports it.  Every entry point has
+the signature of include/mellon_b200.h and receives exactly the ctypes objects backend.py passes.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+from scipy.linalg import solve_triangular
+
+from mellon_b200 import _native as nat
+from mellon_b200.backend import CudaBackend
+
+
+def _val(h):
+    return h.value if hasattr(h, "value") else int(h)
+
+
+def _host(p, n):
+    """View n doubles at a host pointer (c_void_p)."""
+    if n == 0:
+        return np.zeros(0)
+    return np.ctypeslib.as_array((C.c_double * n).from_address(_val(p)))
+
+
+def _prog_of(ref):
+    return ref._obj if hasattr(ref, "_obj") else ref
+
+
+def eval_program(prog, x, y):
+    """Interpret an ``mb_kprog`` in NumPy with the arithmetic of util.py:351-366 and cov.py."""
+    stack = []
+    for i in range(prog.n_ops):
+        o = prog.ops[i]
+        if o.op == nat.OP_LEAF:
+            if o.dim_cnt < 0:
+                xs, ys = x, y
+            else:
+                dims = [prog.dims[o.dim_off + k] for k in range(o.dim_cnt)]
+                xs, ys = x[:, dims], y[:, dims]
+            if o.kind == nat.K_LINEAR:
+                stack.append(xs @ ys.T / o.ls)
+                continue
+            xx = np.sum(xs * xs, axis=1)[:, None]
+            yy = np.sum(ys * ys, axis=1)[None, :]
+            dist = np.sqrt(np.maximum(xx - 2 * (xs @ ys.T) + yy + 1e-12, 0))
+            if o.kind == 6:
+                stack.append(dist)
+                continue
+            r = dist / o.ls
+            if o.kind == nat.K_MATERN32:
+                r = np.sqrt(3.0) * r
+                stack.append((r + 1) * np.exp(-r))
+            elif o.kind == nat.K_MATERN52:
+                r = np.sqrt(5.0) * r
+                stack.append((r + r * r / 3 + 1) * np.exp(-r))
+            elif o.kind == nat.K_EXPQUAD:
+                stack.append(np.exp(-r * r / 2))
+            elif o.kind == nat.K_EXPONENTIAL:
+                stack.append(np.exp(-r / 2))
+            elif o.kind == nat.K_RATQUAD:
+                stack.append((r * r / (2 * o.alpha) + 1) ** -o.alpha)
+            else:
+                raise ValueError(f"unknown kernel kind {o.kind}")
+        elif o.op == nat.OP_CONST:
+            stack.append(o.value)
+        elif o.op == nat.OP_POW:
+            stack.append(stack.pop() ** o.value)
+        else:
+            b, a = stack.pop(), stack.pop()
+            stack.append(a + b if o.op == nat.OP_ADD else a * b)
+    (out,) = stack
+    return np.broadcast_to(out, (x.shape[0], y.shape[0])).copy()
+
+
+class FakeLib:
+    def __init__(self, rank=0, world=1):
+        self.m = {}
+        self.next = 1
+        self.rank, self.world = rank, world
+        self.err = b""
+        self.launches = 0
+        self.calls = []
+
+    # ---- helpers ------------------------------------------------------------------------------
+    def A(self, h):
+        return self.m[_val(h)]
+
+    def _new(self, a):
+        k = self.next
+        self.next += 1
+        self.m[k] = np.array(a, dtype=np.float64).reshape(a.shape if a.ndim == 2 else (-1, 1))
+        return k
+
+    def _allreduce(self, a):
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+
+            t = torch.from_numpy(a)
+            dist.all_reduce(t)
+        return a
+
+    def _fail(self, msg, code=-2):
+        self.err = msg.encode()
+        return code
+
+    # ---- context --------------------------------------------------------------------------------
+    def mb_last_error(self):
+        return self.err
+
+    def mb_version(self):
+        return 100
+
+    def mb_ctx_sync(self, ctx):
+        return 0
+
+    def mb_ctx_destroy(self, ctx):
+        return 0
+
+    def mb_ctx_launch_count(self, ctx):
+        return self.launches
+
+    def mb_ctx_info(self, ctx, dev, sm, free, total):
+        dev._obj.value, sm._obj.value, free._obj.value, total._obj.value = 0, 148, 1 << 37, 1 << 37
+        return 0
+
+    def mb_timer_start(self, ctx, slot):
+        import time
+
+        self._t = getattr(self, "_t", {})
+        self._t[slot] = time.perf_counter()
+        return 0
+
+    def mb_timer_stop(self, ctx, slot, ms):
+        import time
+
+        ms._obj.value = (time.perf_counter() - self._t[slot]) * 1e3
+        return 0
+
+    def mb_flush_l2(self, ctx):
+        return 0
+
+    def mb_set_option(self, ctx, key, value):
+        return 0
+
+    def mb_prof_enable(self, ctx, on):
+        return 0
+
+    def mb_prof_reset(self, ctx):
+        return 0
+
+    def mb_prof_read(self, ctx, cls, count, ms, work):
+        count._obj.value, ms._obj.value, work._obj.value = 0, 0.0, 0.0
+        return 0
+
+    def mb_comm_info(self, ctx, rank, world):
+        rank._obj.value, world._obj.value = self.rank, self.world
+        return 0
+
+    def mb_comm_allreduce(self, ctx, a):
+        self._allreduce(self.A(a))
+        return 0
+
+    def mb_comm_allgather(self, ctx, a, out):
+        src, dst = self.A(a), self.A(out)
+        if self.world == 1:
+            dst[...] = src
+            return 0
+        import torch
+        import torch.distributed as dist
+
+        parts = [torch.empty(src.shape, dtype=torch.float64) for _ in range(self.world)]
+        dist.all_gather(parts, torch.from_numpy(np.ascontiguousarray(src)))
+        dst[...] = np.concatenate([p.numpy() for p in parts], axis=0)
+        return 0
+
+    # ---- matrices -------------------------------------------------------------------------------
+    def mb_mat_alloc(self, ctx, rows, cols, out):
+        if rows < 0 or cols < 0:
+            return self._fail("negative shape")
+        out._obj.value = self._new(np.full((rows, cols), np.nan))
+        return 0
+
+    def mb_mat_free(self, ctx, h):
+        self.m.pop(_val(h), None)
+        return 0
+
+    def mb_mat_upload(self, ctx, h, host, row0, nrows):
+        a = self.A(h)
+        a[row0:row0 + nrows] = _host(host, nrows * a.shape[1]).reshape(nrows, a.shape[1])
+        return 0
+
+    def mb_mat_download(self, ctx, h, host, row0, nrows):
+        a = self.A(h)
+        _host(host, nrows * a.shape[1])[:] = a[row0:row0 + nrows].ravel()
+        return 0
+
+    def mb_mat_copy(self, ctx, src, dst):
+        self.A(dst)[...] = self.A(src)
+        return 0
+
+    def mb_mat_fill(self, ctx, h, v):
+        self.A(h)[...] = v
+        return 0
+
+    def mb_mat_transpose(self, ctx, src, dst):
+        self.A(dst)[...] = self.A(src).T
+        return 0
+
+    def mb_mat_add_diag(self, ctx, h, v):
+        a = self.A(h)
+        a[np.diag_indices(a.shape[0])] += v
+        return 0
+
+    def mb_mat_scale_cols(self, ctx, h, s):
+        self.A(h)[...] *= self.A(s).ravel()[None, :]
+        return 0
+
+    def mb_mat_copy_cols(self, ctx, src, c0, ncols, dst):
+        self.A(dst)[...] = self.A(src)[:, c0:c0 + ncols]
+        return 0
+
+    def mb_mat_symmetrize(self, ctx, h):
+        a = self.A(h)
+        a[...] = np.tril(a) + np.tril(a, -1).T
+        return 0
+
+    def mb_mat_scale(self, ctx, h, s):
+        self.A(h)[...] *= s
+        return 0
+
+    def mb_mat_row_sumsq(self, ctx, a, out):
+        self.A(out)[:, 0] = np.sum(self.A(a) ** 2, axis=1)
+        return 0
+
+    # ---- covariance -----------------------------------------------------------------------------
+    def mb_cov_build(self, ctx, prog, x, y, K):
+        self.launches += 1
+        self.calls.append("mb_cov_build")
+        self.A(K)[...] = eval_program(_prog_of(prog), self.A(x), self.A(y))
+        return 0
+
+    def mb_cov_diag(self, ctx, prog, x, out):
+        xa = self.A(x)
+        p = _prog_of(prog)
+        self.A(out)[:, 0] = [eval_program(p, xa[i:i + 1], xa[i:i + 1])[0, 0] for i in range(xa.shape[0])]
+        return 0
+
+    def mb_cov_matvec(self, ctx, prog, xq, base, w, mu, out):
+        self.launches += 1
+        self.A(out)[...] = mu + eval_program(_prog_of(prog), self.A(xq), self.A(base)) @ self.A(w)
+        return 0
+
+    def mb_predict_mean(self, ctx, prog, xq, nq, d, base, w, mu, out):
+        self.launches += 1
+        self.calls.append("mb_predict_mean")
+        b = self.A(base)
+        if d != b.shape[1]:
+            return self._fail("feature mismatch")
+        q = _host(xq, nq * d).reshape(nq, d)
+        wv = self.A(w)
+        _host(out, nq * wv.shape[1])[:] = (mu + eval_program(_prog_of(prog), q, b) @ wv).ravel()
+        return 0
+
+    def mb_nn_distances(self, ctx, x, allp, self_offset, dist, idx_host):
+        xa, ya = self.A(x), self.A(allp)
+        d2 = ((xa[:, None, :] - ya[None, :, :]) ** 2).sum(-1)
+        d2[np.arange(xa.shape[0]), np.arange(xa.shape[0]) + self_offset] = np.inf
+        j = np.argmin(d2, axis=1)
+        self.A(dist)[:, 0] = np.sqrt(d2[np.arange(xa.shape[0]), j])
+        if _val(idx_host):
+            np.ctypeslib.as_array((C.c_int64 * xa.shape[0]).from_address(_val(idx_host)))[:] = j
+        return 0
+
+    # ---- factorisations / solves ----------------------------------------------------------------
+    def mb_potrf(self, ctx, h):
+        self.launches += 1
+        a = self.A(h)
+        sym = np.tril(a) + np.tril(a, -1).T
+        try:
+            a[...] = np.linalg.cholesky(sym)
+            return 0
+        except np.linalg.LinAlgError:
+            a[...] = np.nan
+            return 1
+
+    def mb_cov_chol(self, ctx, prog, xu, diag_add, Lp):
+        self.calls.append("mb_cov_chol")
+        self.mb_cov_build(ctx, prog, xu, xu, Lp)
+        self.mb_mat_add_diag(ctx, Lp, diag_add)
+        return self.mb_potrf(ctx, Lp)
+
+    def mb_trsm_right_lt(self, ctx, Lp, X):
+        self.launches += 1
+        x = self.A(X)
+        if x.size:
+            x[...] = solve_triangular(self.A(Lp), x.T, lower=True).T
+        return 0
+
+    def mb_tri_solve(self, ctx, Lp, trans, B):
+        b = self.A(B)
+        L = self.A(Lp)
+        b[...] = solve_triangular(L.T if trans else L, b, lower=not trans)
+        return 0
+
+    def mb_lowrank_standard(self, ctx, prog, x, xu, Lp, L):
+        self.mb_cov_build(ctx, prog, x, xu, L)
+        return self.mb_trsm_right_lt(ctx, Lp, L)
+
+    def mb_gram(self, ctx, L, G):
+        self.launches += 1
+        self.calls.append("mb_gram")
+        l = self.A(L)
+        g = l.T @ l
+        self.A(G)[...] = self._allreduce(g)
+        return 0
+
+    def mb_gemv_t(self, ctx, L, t, b):
+        v = self.A(L).T @ self.A(t).ravel()
+        self.A(b)[...] = self._allreduce(v).reshape(self.A(b).shape)
+        return 0
+
+    def mb_ridge_init(self, ctx, L, t, z0):
+        self.calls.append("mb_ridge_init")
+        l = self.A(L)
+        g = self._allreduce(l.T @ l) + np.eye(l.shape[1])
+        b = self._allreduce(l.T @ self.A(t).ravel())
+        _host(z0, l.shape[1])[:] = np.linalg.solve(g, b)
+        return 0
+
+    def mb_gemm(self, ctx, ta, tb, alpha, A, B, beta, Cm):
+        self.launches += 1
+        a, b, c = self.A(A), self.A(B), self.A(Cm)
+        prod = alpha * ((a.T if ta else a) @ (b.T if tb else b))
+        c[...] = prod + (beta * c if beta != 0.0 else 0.0)
+        return 0
+
+    # ---- objective ------------------------------------------------------------------------------
+    def mb_loss_grad(self, ctx, L, V, sum_vdr, mu, k, z, loss, grad):
+        self.launches += 1
+        self.calls.append("mb_loss_grad")
+        l = self.A(L)
+        r = l.shape[1]
+        zv = _host(z, r).copy()
+        f = l @ zv + mu
+        Aexp = np.exp(f + self.A(V).ravel())
+        part = np.concatenate([l.T @ (Aexp - 1.0), [np.sum(f - Aexp)]])
+        part = self._allreduce(part)
+        _host(grad, r)[:] = zv + part[:r]
+        loss._obj.value = 0.5 * float(zv @ zv) + 0.5 * k * np.log(2 * np.pi) - (part[r] + sum_vdr)
+        return 0
+
+    def mb_transform(self, ctx, L, z, mu, f):
+        l = self.A(L)
+        _host(f, l.shape[0])[:] = l @ _host(z, l.shape[1]) + mu
+        return 0
+
+    def mb_hess_diag(self, ctx, L, V, mu, z, diag):
+        l = self.A(L)
+        r = l.shape[1]
+        Aexp = np.exp(l @ _host(z, r) + mu + self.A(V).ravel())
+        d = self._allreduce(np.einsum("i,ij,ij->j", Aexp, l, l))
+        _host(diag, r)[:] = 1.0 + d
+        return 0
+
+    def mb_syevd(self, ctx, a, w):
+        m = self.A(a)
+        ev, vec = np.linalg.eigh(np.tril(m) + np.tril(m, -1).T)
+        m[...] = vec
+        self.A(w)[:, 0] = ev
+        return 0
+
+    def mb_host_alloc(self, nbytes, out):
+        buf = (C.c_char * max(int(nbytes), 1))()
+        self._keep = getattr(self, "_keep", [])
+        self._keep.append(buf)
+        out._obj.value = C.addressof(buf)
+        return 0
+
+
+class FakeBackend(CudaBackend):
+    """CudaBackend with the shared library swapped for :class:`FakeLib` (host logic is untouched)."""
+
+    name = "fake"
+
+    def __init__(self, rank=0, world=1):
+        self.lib = FakeLib(rank, world)
+        self.ctx = C.c_void_p(1)
+        self.device = 0
+        self.rank, self.world = rank, world
+        self._progs = {}
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def close(self):
+        self.ctx = None

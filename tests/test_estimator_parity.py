@@ -10,7 +10,6 @@ import mellon_b200 as mb
 from mellon_b200 import cov as C
 from oracle import mellon_oracle as O
 
-pytestmark = pytest.mark.gpu
 
 TOL = 1e-5          # north_star: log-density within 1e-5 relative
 TIGHT_TOL = 1e-6    # both optimisers run to convergence: same optimum

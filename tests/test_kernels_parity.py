@@ -9,7 +9,6 @@ import mellon_b200 as mb
 from mellon_b200 import cov as C
 from oracle import mellon_oracle as O
 
-pytestmark = pytest.mark.gpu
 
 
 def rel_err(a, b):
