@@ -59,6 +59,7 @@ extern "C" int mb_ctx_destroy(mb_ctx* c) {
   mb_comm_destroy(c);
   if (c->scratch) cudaFree(c->scratch);
   if (c->flush_buf) cudaFree(c->flush_buf);
+  if (c->gemm_ws) cudaFree(c->gemm_ws);
   if (c->pinned) cudaFreeHost(c->pinned);
   prof_resolve(c);
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);

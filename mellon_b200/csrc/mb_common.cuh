@@ -42,13 +42,15 @@ struct mb_ctx {
   size_t pinned_bytes = 0;
   double* flush_buf = nullptr;
   size_t flush_bytes = 0;
+  double* gemm_ws = nullptr;           // split-k partial tiles (own buffer: GEMMs run inside scratch users)
+  size_t gemm_ws_bytes = 0;
   // NCCL
   void* comm = nullptr;
   int rank = 0, world = 1;
   // options
   int opt_gemm = 0;      // 0 = DMMA tiles (default), 1 = DFMA register tiles
-  int opt_cov = 0;       // 0 = default tile kernel
-  int opt_lossgrad = 0;  // 0 = fused single pass, 1 = two-pass
+  int opt_cov = 0;       // 0 = DMMA tile kernel (exp-family leaf) else 1; 1 = DFMA register-tile kernel; 2 = general kernel
+  int opt_lossgrad = 0;  // 0 = TMA-ring streaming single pass, 1 = two-pass, 2 = register-fused single pass
   // per-kernel-class stopwatch
   bool prof_on = false;
   std::vector<mb_prof_span> prof_spans;      // recorded, not yet resolved

@@ -12,6 +12,7 @@
 // double-buffered); 8x4 register micro-tiles accumulate x.y on the FP64 pipe; the epilogue
 // evaluates the kernel in registers.
 #include "mb_common.cuh"
+#include "mb_math.cuh"
 
 namespace {
 
@@ -192,7 +193,7 @@ __device__ __forceinline__ double eval_program(const DevProgram& P, const double
 
 // ---- packing: gather a leaf's active columns, zero-pad to ldp, squared row norms ------------
 __global__ void pack_kernel(const double* __restrict__ a, int64_t n, int64_t cols, const int* __restrict__ dims,
-                            int d, int ldp, double* __restrict__ packed, double* __restrict__ norm) {
+                            int d, int ldp, double scale, double* __restrict__ packed, double* __restrict__ norm) {
   // one warp per row
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -201,7 +202,7 @@ __global__ void pack_kernel(const double* __restrict__ a, int64_t n, int64_t col
     double s = 0.0;
     for (int c = lane; c < ldp; c += 32) {
       double v = 0.0;
-      if (c < d) v = a[i * cols + (dims ? dims[c] : c)];
+      if (c < d) v = a[i * cols + (dims ? dims[c] : c)] * scale;
       if (packed) packed[i * ldp + c] = v;
       s = fma(v, v, s);
     }
@@ -409,6 +410,178 @@ cov_tile_kernel(const double* __restrict__ xp, const double* __restrict__ xnorm,
   }
 }
 
+
+// ---- tensor-pipe path: one leaf of the exponential family --------------------------------------
+// The x.y contraction runs as FP64 MMA (mma.sync m8n8k4, DMMA) on operands that the pack kernel
+// has pre-scaled by the leaf's distance scale (sqrt(5)/ls for Matern52, ...), so the accumulator is
+// the scaled dot product and sq' = xn + yn - 2 acc is already (r_scaled)^2.  DMMA shares the FP64
+// pipe with DFMA (tools/microbench_fp64: 37.1 TF either way, no overlap) but needs 12 shared-memory
+// loads per 16 MMAs instead of 12 per 64 FMAs, which is what bounded the register-tile kernel.
+// The epilogue is the lean sqrt / exp of mb_math.cuh (23 FP64 instructions per Matern52 element).
+//
+// CTA = 128 cells x 64 landmarks, 8 warps as 4 x 2, warp tile 32 x 32 = 4 x 4 MMA tiles; the cell
+// panel and the double-buffered landmark tiles arrive by 1-D bulk TMA; two CTAs share an SM.
+constexpr int MBM = 128, MBN = 64, MNT = 256;
+__device__ const double g_exp2_tab[64] = MB_EXP2_TABLE_INIT;
+
+template <int KIND>
+__device__ __forceinline__ double eval_scaled(double sq, const double* tab, double alpha) {
+  sq = mbmath::clamp_tiny(sq);
+  if (KIND == MB_K_EXPQUAD) return mbmath::exp_neg(sq, tab);
+  const double r = mbmath::sqrt_pos(sq);
+  const double e = mbmath::exp_neg(r, tab);
+  if (KIND == MB_K_EXPONENTIAL) return e;
+  if (KIND == MB_K_MATERN32) return fma(r, e, e);
+  return fma(fma(r, 1.0 / 3.0, 1.0), r, 1.0) * e;  // MATERN52
+}
+
+template <int KIND, int MODE>
+__global__ void __launch_bounds__(MNT, 2)
+cov_mma_kernel(const double* __restrict__ xp, const double* __restrict__ xnorm, int64_t n,
+               const double* __restrict__ yp, const double* __restrict__ ynorm, int64_t m, int ldp, double eps_scaled,
+               double* __restrict__ out, int64_t ldo, const double* __restrict__ w, double mu) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* xs = reinterpret_cast<double*>(smem_raw);
+  double* ys0 = xs + (size_t)MBM * ldp;
+  double* ys1 = ys0 + (size_t)MBN * ldp;
+  __shared__ __align__(8) uint64_t bar_x, bar_y[2];
+  __shared__ double tab[64];
+  __shared__ double mv_red[2][MBM];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lk = lane & 3;
+  const int wr0 = (warp >> 1) * 32, wc0 = (warp & 1) * 32;
+
+  if (tid < 64) tab[tid] = g_exp2_tab[tid];
+  for (int e = tid; e < (MBM + 2 * MBN) * ldp; e += MNT) xs[e] = 0.0;
+  if (tid == 0) {
+    mbar_init(&bar_x, 1);
+    mbar_init(&bar_y[0], 1);
+    mbar_init(&bar_y[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  __syncthreads();
+
+  uint32_t px = 0, py0 = 0, py1 = 0;
+  const int64_t n_panels = (n + MBM - 1) / MBM;
+  const int64_t n_ytiles = (m + MBN - 1) / MBN;
+  const uint32_t row_bytes = (uint32_t)ldp * 8u;
+  const bool vec_store = (MODE == MODE_STORE) && ((ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+
+  for (int64_t panel = blockIdx.x; panel < n_panels; panel += gridDim.x) {
+    const int64_t row0 = panel * MBM;
+    const int rows_valid = (int)min((int64_t)MBM, n - row0);
+    if (tid == 0) {
+      mbar_expect_tx(&bar_x, rows_valid * row_bytes);
+      bulk_g2s(xs, xp + row0 * ldp, rows_valid * row_bytes, &bar_x);
+      const int cv = (int)min((int64_t)MBN, m);
+      mbar_expect_tx(&bar_y[0], cv * row_bytes);
+      bulk_g2s(ys0, yp, cv * row_bytes, &bar_y[0]);
+    }
+    double xn[4], rowacc[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int64_t r = row0 + wr0 + i * 8 + lr;
+      xn[i] = (r < n) ? xnorm[r] + eps_scaled : 0.0;
+      rowacc[i] = 0.0;
+    }
+    mbar_wait(&bar_x, px);
+    px ^= 1;
+
+    for (int64_t jt = 0; jt < n_ytiles; jt++) {
+      const int buf = (int)(jt & 1);
+      if (tid == 0 && jt + 1 < n_ytiles) {
+        const int64_t c0n = (jt + 1) * MBN;
+        const int cv = (int)min((int64_t)MBN, m - c0n);
+        uint64_t* b = buf ? &bar_y[0] : &bar_y[1];
+        mbar_expect_tx(b, cv * row_bytes);
+        bulk_g2s(buf ? ys0 : ys1, yp + c0n * ldp, cv * row_bytes, b);
+      }
+      const int64_t col0 = jt * MBN;
+      // norms / weights of this thread's 8 columns (in flight while the tile is awaited)
+      double yn[4][2], wv[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int64_t c = col0 + wc0 + j * 8 + 2 * lk + h;
+          yn[j][h] = (c < m) ? ynorm[c] : 0.0;
+          if (MODE == MODE_MATVEC) wv[j][h] = (c < m) ? w[c] : 0.0;
+        }
+      if (buf == 0) { mbar_wait(&bar_y[0], py0); py0 ^= 1; }
+      else          { mbar_wait(&bar_y[1], py1); py1 ^= 1; }
+      const double* ys = buf ? ys1 : ys0;
+
+      double acc[4][4][2];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+      const double* xb = xs + (size_t)(wr0 + lr) * ldp + lk;
+      const double* yb = ys + (size_t)(wc0 + lr) * ldp + lk;
+      const int step8 = 8 * ldp;
+#pragma unroll 2
+      for (int k = 0; k < ldp; k += 4) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) af[i] = xb[i * step8 + k];
+#pragma unroll
+        for (int j = 0; j < 4; j++) bf[j] = yb[j * step8 + k];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                         : "d"(af[i]), "d"(bf[j]));
+      }
+
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int64_t r = row0 + wr0 + i * 8 + lr;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int64_t c = col0 + wc0 + j * 8 + 2 * lk;
+          const double v0 = eval_scaled<KIND>(fma(-2.0, acc[i][j][0], xn[i] + yn[j][0]), tab, 0.0);
+          const double v1 = eval_scaled<KIND>(fma(-2.0, acc[i][j][1], xn[i] + yn[j][1]), tab, 0.0);
+          if (MODE == MODE_STORE) {
+            if (r < n) {
+              double* o = out + r * ldo + c;
+              if (vec_store && c + 1 < m) {
+                *reinterpret_cast<double2*>(o) = make_double2(v0, v1);
+              } else {
+                if (c < m) o[0] = v0;
+                if (c + 1 < m) o[1] = v1;
+              }
+            }
+          } else {
+            rowacc[i] = fma(v1, wv[j][1], fma(v0, wv[j][0], rowacc[i]));  // wv = 0 beyond m
+          }
+        }
+      }
+      __syncthreads();  // everyone is done with ys[buf] (and xs on the last tile)
+    }
+
+    if (MODE == MODE_MATVEC) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        double s = rowacc[i];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (lk == 0) mv_red[warp & 1][wr0 + i * 8 + lr] = s;
+      }
+      __syncthreads();
+      if (tid < MBM) {
+        const int64_t r = row0 + tid;
+        if (r < n) out[r * ldo] = mu + (mv_red[0][tid] + mv_red[1][tid]);
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // exact Euclidean distance of each row to its selected neighbour: sqrt(sum (x_i - y_j)^2), one warp per row
 __global__ void nn_exact_kernel(const double* __restrict__ x, int64_t n, const double* __restrict__ y, int d,
                                 const int64_t* __restrict__ idx, double* __restrict__ out) {
@@ -554,7 +727,28 @@ int ldp_for(int d) {
   return l;
 }
 
+// leading dimension of the DMMA operand tiles: a multiple of 4 (k-step) that is 4 mod 8, so the 8 rows x 4 k
+// fragment loads of a half-warp fall into 16 distinct 8-byte banks
+int ldp_mma(int d) {
+  int l = (d + 3) & ~3;
+  if ((l & 7) == 0) l += 4;
+  return l;
+}
+
+// distance scale folded into the packed operands of the tensor-pipe path (0 => kind not handled there)
+double mma_scale(const Leaf& l) {
+  switch (l.kind) {
+    case MB_K_MATERN32: return sqrt(3.0) / l.ls;
+    case MB_K_MATERN52: return sqrt(5.0) / l.ls;
+    case MB_K_EXPQUAD: return sqrt(0.5) / l.ls;
+    case MB_K_EXPONENTIAL: return 0.5 / l.ls;
+    default: return 0.0;
+  }
+}
+
 struct Plan {
+  bool mma = false;      // single exponential-family leaf: operands packed pre-scaled for cov_mma_kernel
+  double eps_scaled = 0.0;  // 1e-12 * scale^2
   bool same = false;  // y is x (symmetric landmark covariance)
   double in_cols = 0.0;  // columns of the input matrices
   Program prog;
@@ -564,7 +758,7 @@ struct Plan {
 };
 
 // Lay out scratch and pack every leaf's operands.  `same` => y is x (pack once).
-int prepare(mb_ctx* ctx, const mb_kprog* kp, const mb_mat* x, const mb_mat* y, Plan* plan) {
+int prepare(mb_ctx* ctx, const mb_kprog* kp, const mb_mat* x, const mb_mat* y, Plan* plan, bool allow_mma = false) {
   MB_CHECK(x->cols == y->cols, "covariance inputs have %lld and %lld columns", (long long)x->cols,
            (long long)y->cols);
   MB_TRY(parse_program(kp, x->cols, &plan->prog));
@@ -573,6 +767,17 @@ int prepare(mb_ctx* ctx, const mb_kprog* kp, const mb_mat* x, const mb_mat* y, P
   plan->same = same;
   plan->in_cols = (double)x->cols;
   const int nl = (int)plan->prog.leaves.size();
+  double scale = 1.0;
+  if (allow_mma && ctx->opt_cov == 0 && nl == 1 && plan->prog.n_ops == 1) {
+    const Leaf& lf = plan->prog.leaves[0];
+    const int d0 = lf.all_dims ? (int)x->cols : (int)lf.dims.size();
+    const double sc = mma_scale(lf);
+    if (sc > 0.0 && (size_t)(MBM + 2 * MBN) * ldp_mma(d0) * sizeof(double) <= 100 * 1024) {
+      plan->mma = true;
+      plan->eps_scaled = 1e-12 * sc * sc;
+      scale = sc;
+    }
+  }
   size_t total = 0;
   std::vector<size_t> off_xp(nl), off_xn(nl), off_yp(nl), off_yn(nl), off_dims(nl);
   std::vector<bool> direct(nl);
@@ -580,8 +785,8 @@ int prepare(mb_ctx* ctx, const mb_kprog* kp, const mb_mat* x, const mb_mat* y, P
     const Leaf& lf = plan->prog.leaves[l];
     int d = lf.all_dims ? (int)x->cols : (int)lf.dims.size();
     MB_CHECK(d > 0, "covariance leaf with zero active dims");
-    int ldp = ldp_for(d);
-    direct[l] = lf.all_dims && ldp == d;
+    int ldp = plan->mma ? ldp_mma(d) : ldp_for(d);
+    direct[l] = !plan->mma && lf.all_dims && ldp == d;
     auto take = [&](size_t doubles) {
       size_t o = total;
       total += (doubles + 15) & ~(size_t)15;
@@ -602,7 +807,7 @@ int prepare(mb_ctx* ctx, const mb_kprog* kp, const mb_mat* x, const mb_mat* y, P
   for (int l = 0; l < nl; l++) {
     const Leaf& lf = plan->prog.leaves[l];
     int d = lf.all_dims ? (int)x->cols : (int)lf.dims.size();
-    int ldp = ldp_for(d);
+    int ldp = plan->mma ? ldp_mma(d) : ldp_for(d);
     int* dims_dev = nullptr;
     if (!lf.all_dims) {
       dims_dev = reinterpret_cast<int*>(s + off_dims[l]);
@@ -613,7 +818,7 @@ int prepare(mb_ctx* ctx, const mb_kprog* kp, const mb_mat* x, const mb_mat* y, P
       double* norm = s + offn;
       if (a->rows > 0) {
         int grid = (int)min((int64_t)ctx->n_sm * 8, ceil_div64(a->rows, 8));
-        MB_LAUNCH(ctx, pack_kernel, grid, 256, 0, a->p, a->rows, a->cols, dims_dev, d, ldp, packed, norm);
+        MB_LAUNCH(ctx, pack_kernel, grid, 256, 0, a->p, a->rows, a->cols, dims_dev, d, ldp, scale, packed, norm);
       }
       o->p = direct[l] ? a->p : packed;
       o->norm = norm;
@@ -685,6 +890,44 @@ int launch_fast(mb_ctx* ctx, const Plan& plan, int64_t n, int64_t m, double* out
   return 0;
 }
 
+
+template <int MODE>
+int launch_mma(mb_ctx* ctx, const Plan& plan, int64_t n, int64_t m, double* out, int64_t ldo, const double* w,
+               double mu, bool* done) {
+  *done = false;
+  if (!plan.mma) return 0;
+  const Operand& xo = plan.xo[0];
+  const Operand& yo = plan.yo[0];
+  const int ldp = xo.ldp;
+  const size_t smem = (size_t)(MBM + 2 * MBN) * ldp * sizeof(double);
+  const int kind = plan.dprog.leaf[0].kind;
+  const int64_t n_panels = ceil_div64(n, MBM);
+  const int grid = (int)min(n_panels, (int64_t)ctx->n_sm * 2);
+  const int prof_cls = prof_class<MODE>(ctx, plan, n, m);
+#define MB_MMA_CASE(K)                                                                                       \
+  case K: {                                                                                                  \
+    static bool cfg = false;                                                                                 \
+    if (!cfg) {                                                                                              \
+      MB_CUDA(cudaFuncSetAttribute(cov_mma_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                   100 * 1024));                                                             \
+      cfg = true;                                                                                            \
+    }                                                                                                        \
+    MB_LAUNCH_P(ctx, prof_cls, (cov_mma_kernel<K, MODE>), grid, MNT, smem, xo.p, xo.norm, n, yo.p, yo.norm, m, ldp, \
+                plan.eps_scaled, out, ldo, w, mu);                                                           \
+    break;                                                                                                   \
+  }
+  switch (kind) {
+    MB_MMA_CASE(MB_K_MATERN32)
+    MB_MMA_CASE(MB_K_MATERN52)
+    MB_MMA_CASE(MB_K_EXPQUAD)
+    MB_MMA_CASE(MB_K_EXPONENTIAL)
+    default: return 0;
+  }
+#undef MB_MMA_CASE
+  *done = true;
+  return 0;
+}
+
 template <int MODE>
 int launch_general(mb_ctx* ctx, const Plan& plan, int64_t n, int64_t m, double* out, int64_t ldo, const double* w,
                    double mu) {
@@ -706,9 +949,10 @@ int launch_general(mb_ctx* ctx, const Plan& plan, int64_t n, int64_t m, double* 
 int cov_build_impl(mb_ctx* ctx, const mb_kprog* prog, const mb_mat* x, const mb_mat* y, double* out, int64_t ldo) {
   if (x->rows == 0 || y->rows == 0) return 0;
   Plan plan;
-  MB_TRY(prepare(ctx, prog, x, y, &plan));
+  MB_TRY(prepare(ctx, prog, x, y, &plan, true));
   bool done = false;
-  if (ctx->opt_cov == 0) MB_TRY(launch_fast<MODE_STORE>(ctx, plan, x->rows, y->rows, out, ldo, nullptr, 0.0, &done));
+  MB_TRY(launch_mma<MODE_STORE>(ctx, plan, x->rows, y->rows, out, ldo, nullptr, 0.0, &done));
+  if (!done && ctx->opt_cov != 2) MB_TRY(launch_fast<MODE_STORE>(ctx, plan, x->rows, y->rows, out, ldo, nullptr, 0.0, &done));
   if (!done) MB_TRY(launch_general<MODE_STORE>(ctx, plan, x->rows, y->rows, out, ldo, nullptr, 0.0));
   return 0;
 }
@@ -751,9 +995,10 @@ extern "C" int mb_cov_matvec(mb_ctx* ctx, const mb_kprog* prog, const mb_mat* xq
   const int64_t p = w->cols;
   if (p == 1) {
     Plan plan;
-    MB_TRY(prepare(ctx, prog, xq, base, &plan));
+    MB_TRY(prepare(ctx, prog, xq, base, &plan, true));
     bool done = false;
-    if (ctx->opt_cov == 0)
+    MB_TRY(launch_mma<MODE_MATVEC>(ctx, plan, xq->rows, base->rows, out->p, 1, w->p, mu, &done));
+    if (!done && ctx->opt_cov != 2)
       MB_TRY(launch_fast<MODE_MATVEC>(ctx, plan, xq->rows, base->rows, out->p, 1, w->p, mu, &done));
     if (!done) MB_TRY(launch_general<MODE_MATVEC>(ctx, plan, xq->rows, base->rows, out->p, 1, w->p, mu));
     return 0;

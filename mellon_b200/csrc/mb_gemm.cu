@@ -6,12 +6,14 @@
 //   A(i,k) = A[i*lda + k] (AK=false)  or  A[k*lda + i] (AK=true,  "k-major")
 //   B(j,k) = B[j*ldb + k] (BK=false)  or  B[k*ldb + j] (BK=true)
 //
-// CTA tile 128x128x16, 8 warps (2 x 4), warp tile 64x32 = 8x4 DMMA tiles.
+// CTA tile 128x128x16; 16 warps (4 x 4), warp tile 32x32 = 4x4 DMMA tiles (default) or 8 warps (2 x 4),
+// warp tile 64x32 (opt_gemm = 2).  Symmetric (lower-only) products split the long k axis so that
+// tiles x splits fills whole waves of 148 CTAs; the partial tiles are summed in a fixed order.
 #include "mb_common.cuh"
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BKT = 16, STAGES = 3, NTHREADS = 256;
+constexpr int BM = 128, BN = 128, BKT = 16, STAGES = 3;
 constexpr int LD_ROWMAJ = BKT + 4;   // [tile_rows][BKT+4]   (stride 20: 4*m + k distinct mod 16)
 constexpr int LD_KMAJ = BM + 4;      // [BKT][tile_rows+4]   (stride 132: 4*k + m distinct mod 16)
 constexpr int TILE_DOUBLES = BM * LD_ROWMAJ;  // 2560 >= BKT * LD_KMAJ (2112)
@@ -40,7 +42,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // Load one operand tile (tile_rows = 128 "row" indices x BKT k indices) into shared memory.
 // KMAJ=false: source element (r, k) at src[(r0+r)*ld + k0+k]  -> dst[r*LD_ROWMAJ + k]
 // KMAJ=true : source element (r, k) at src[(k0+k)*ld + r0+r]  -> dst[k*LD_KMAJ + r]
-template <bool KMAJ>
+template <bool KMAJ, int NTHREADS>
 __device__ __forceinline__ void load_tile(double* dst, const double* __restrict__ src, int64_t ld,
                                           int64_t r0, int64_t nr, int64_t k0, int64_t nk, bool vec_ok,
                                           int tid) {
@@ -99,18 +101,26 @@ __device__ __forceinline__ void load_tile(double* dst, const double* __restrict_
   }
 }
 
-template <bool AK, bool BK>
-__global__ void __launch_bounds__(NTHREADS, 1)
-gemm_dmma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __restrict__ A, int64_t lda,
+template <bool AK, bool BK, int WARPS_M>
+__global__ void __launch_bounds__(WARPS_M * 128, 1)
+gemm_dmma_kernel(int64_t m, int64_t n, int64_t k_total, double alpha, const double* __restrict__ A, int64_t lda,
                  const double* __restrict__ B, int64_t ldb, double beta, double* __restrict__ C,
-                 int64_t ldc, int lower_only, int64_t tiles_n, int64_t n_tiles, int a_vec, int b_vec) {
+                 int64_t ldc, int lower_only, int64_t tiles_n, int64_t n_tiles, int a_vec, int b_vec,
+                 int ksplit, int64_t kchunk, double* __restrict__ ws, int64_t ws_stride) {
+  constexpr int NTHREADS = WARPS_M * 128;
+  constexpr int WTM = BM / WARPS_M;  // warp tile rows: 64 or 32
+  constexpr int MI = WTM / 8;
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
+  const int wm0 = (warp >> 2) * WTM, wn0 = (warp & 3) * 32;
   const int lr = lane >> 2, lk = lane & 3;
-  const int64_t nkt = (k + BKT - 1) / BKT;
 
-  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+  for (int64_t item = blockIdx.x; item < n_tiles * ksplit; item += gridDim.x) {
+    const int64_t t = item / ksplit;
+    const int ss = (int)(item % ksplit);
+    const int64_t kbeg = ss * kchunk;
+    const int64_t k = min(k_total, kbeg + kchunk);  // this item contracts [kbeg, k)
+    const int64_t nkt = (k - kbeg + BKT - 1) / BKT;
     int64_t bi, bj;
     if (lower_only) {
       // t enumerates (bi, bj) with bj <= bi, row by row
@@ -124,9 +134,9 @@ gemm_dmma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __
     }
     const int64_t m0 = bi * BM, n0 = bj * BN;
 
-    double acc[8][4][2];
+    double acc[MI][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < MI; i++)
 #pragma unroll
       for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
@@ -136,8 +146,8 @@ gemm_dmma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __
       if (s < nkt) {
         double* sa = smem + (size_t)s * 2 * TILE_DOUBLES;
         double* sb = sa + TILE_DOUBLES;
-        load_tile<AK>(sa, A, lda, m0, m, (int64_t)s * BKT, k, a_vec, tid);
-        load_tile<BK>(sb, B, ldb, n0, n, (int64_t)s * BKT, k, b_vec, tid);
+        load_tile<AK, NTHREADS>(sa, A, lda, m0, m, kbeg + (int64_t)s * BKT, k, a_vec, tid);
+        load_tile<BK, NTHREADS>(sb, B, ldb, n0, n, kbeg + (int64_t)s * BKT, k, b_vec, tid);
       }
       cp_async_commit();
     }
@@ -151,8 +161,8 @@ gemm_dmma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __
           int s = (int)(nt % STAGES);
           double* sa = smem + (size_t)s * 2 * TILE_DOUBLES;
           double* sb = sa + TILE_DOUBLES;
-          load_tile<AK>(sa, A, lda, m0, m, nt * BKT, k, a_vec, tid);
-          load_tile<BK>(sb, B, ldb, n0, n, nt * BKT, k, b_vec, tid);
+          load_tile<AK, NTHREADS>(sa, A, lda, m0, m, kbeg + nt * BKT, k, a_vec, tid);
+          load_tile<BK, NTHREADS>(sb, B, ldb, n0, n, kbeg + nt * BKT, k, b_vec, tid);
         }
         cp_async_commit();
       }
@@ -160,10 +170,10 @@ gemm_dmma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __
       const double* sb = sa + TILE_DOUBLES;
 #pragma unroll
       for (int ks = 0; ks < BKT / 4; ks++) {
-        double af[8], bf[4];
+        double af[MI], bf[4];
         const int kk = ks * 4 + lk;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < MI; i++) {
           int r = wm0 + i * 8 + lr;
           af[i] = AK ? sa[kk * LD_KMAJ + r] : sa[r * LD_ROWMAJ + kk];
         }
@@ -173,7 +183,7 @@ gemm_dmma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __
           bf[j] = BK ? sb[kk * LD_KMAJ + c] : sb[c * LD_ROWMAJ + kk];
         }
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < MI; i++)
 #pragma unroll
           for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
       }
@@ -181,36 +191,38 @@ gemm_dmma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __
     cp_async_wait<0>();
     __syncthreads();
 
-    // epilogue
-    const bool c_vec = ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    // epilogue (split-k items store their raw partial tile into the workspace slice of their split)
+    double* Cout = (ksplit > 1) ? ws + (int64_t)ss * ws_stride : C;
+    const double alpha_e = (ksplit > 1) ? 1.0 : alpha, beta_e = (ksplit > 1) ? 0.0 : beta;
+    const bool c_vec = ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0);
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < MI; i++) {
       int64_t row = m0 + wm0 + i * 8 + lr;
       if (row >= m) continue;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         int64_t col = n0 + wn0 + j * 8 + lk * 2;
         if (col >= n) continue;
-        double* cp = C + row * ldc + col;
-        double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
+        double* cp = Cout + row * ldc + col;
+        double v0 = alpha_e * acc[i][j][0], v1 = alpha_e * acc[i][j][1];
         if (col + 1 < n) {
           if (c_vec) {
-            if (beta != 0.0) {
+            if (beta_e != 0.0) {
               double2 old = *reinterpret_cast<double2*>(cp);
-              v0 += beta * old.x;
-              v1 += beta * old.y;
+              v0 += beta_e * old.x;
+              v1 += beta_e * old.y;
             }
             *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
           } else {
-            if (beta != 0.0) {
-              v0 += beta * cp[0];
-              v1 += beta * cp[1];
+            if (beta_e != 0.0) {
+              v0 += beta_e * cp[0];
+              v1 += beta_e * cp[1];
             }
             cp[0] = v0;
             cp[1] = v1;
           }
         } else {
-          if (beta != 0.0) v0 += beta * cp[0];
+          if (beta_e != 0.0) v0 += beta_e * cp[0];
           cp[0] = v0;
         }
       }
@@ -273,6 +285,20 @@ gemm_dfma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __
   }
 }
 
+// C = alpha * sum_s ws[s] + beta * C over the (lower-triangular tiles of the) output, splits in a fixed order
+__global__ void splitk_reduce_kernel(const double* __restrict__ ws, int ksplit, int64_t ws_stride, int64_t m, int64_t n,
+                                     int64_t ldc, double alpha, double beta, double* __restrict__ C, int lower_only) {
+  const int64_t row = blockIdx.y;
+  const int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= m || col >= n) return;
+  if (lower_only && col / BN > row / BM) return;  // tile never computed
+  double s = 0.0;
+  for (int q = 0; q < ksplit; q++) s += ws[(int64_t)q * ws_stride + row * ldc + col];
+  double v = alpha * s;
+  if (beta != 0.0) v += beta * C[row * ldc + col];
+  C[row * ldc + col] = v;
+}
+
 template <bool AK, bool BK>
 int launch_gemm(mb_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
                 const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only) {
@@ -285,21 +311,56 @@ int launch_gemm(mb_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, cons
   }
   static bool configured = false;
   if (!configured) {
-    MB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    MB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    MB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    MB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    MB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<AK, BK, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    MB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<AK, BK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     configured = true;
   }
   int64_t tm = ceil_div64(m, BM), tn = ceil_div64(n, BN);
   int64_t nt = lower_only ? tm * (tm + 1) / 2 : tm * tn;
   if (lower_only) MB_CHECK(m == n, "gemm lower_only needs a square output");
-  int grid = (int)min(nt, (int64_t)ctx->n_sm);
+  // split the contraction axis when the tile count leaves the last wave of CTAs mostly idle
+  int ksplit = 1;
+  if (lower_only && ctx->opt_gemm != 3 && nt > ctx->n_sm / 2) {
+    double best = (double)nt / (double)(ceil_div64(nt, ctx->n_sm) * ctx->n_sm);
+    for (int sp = 2; sp <= 16 && best < 0.97; sp++) {
+      if (k / sp < 4096) break;
+      const int64_t items = nt * sp;
+      const double eff = (double)items / (double)(ceil_div64(items, ctx->n_sm) * ctx->n_sm);
+      if (eff > best + 0.01) { best = eff; ksplit = sp; }
+    }
+  }
+  int64_t kchunk = k, ws_stride = 0;
+  double* ws = nullptr;
+  if (ksplit > 1) {
+    kchunk = ceil_div64(ceil_div64(k, ksplit), BKT) * BKT;
+    ksplit = (int)ceil_div64(k, kchunk);
+    ws_stride = m * ldc;
+    const size_t need = (size_t)ksplit * ws_stride * sizeof(double);
+    if (need > ctx->gemm_ws_bytes) {
+      MB_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (ctx->gemm_ws) MB_CUDA(cudaFree(ctx->gemm_ws));
+      ctx->gemm_ws = nullptr;
+      ctx->gemm_ws_bytes = 0;
+      MB_CUDA(cudaMalloc(&ctx->gemm_ws, need));
+      ctx->gemm_ws_bytes = need;
+    }
+    ws = ctx->gemm_ws;
+  }
+  int grid = (int)min(nt * ksplit, (int64_t)ctx->n_sm);
   int a_vec = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
   int b_vec = ((ldb & 1) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
   if (ctx->prof_on) ctx->prof_work[MB_PROF_GEMM] += (lower_only ? 1.0 : 2.0) * (double)m * (double)n * (double)k;
-  MB_LAUNCH_P(ctx, MB_PROF_GEMM, (gemm_dmma_kernel<AK, BK>), grid, NTHREADS, SMEM_BYTES, m, n, k, alpha, A, lda, B, ldb, beta,
-            C, ldc, lower_only ? 1 : 0, tn, nt, a_vec, b_vec);
+  if (ctx->opt_gemm == 2) {
+    MB_LAUNCH_P(ctx, MB_PROF_GEMM, (gemm_dmma_kernel<AK, BK, 2>), grid, 256, SMEM_BYTES, m, n, k, alpha, A, lda, B, ldb,
+                beta, C, ldc, lower_only ? 1 : 0, tn, nt, a_vec, b_vec, ksplit, kchunk, ws, ws_stride);
+  } else {
+    MB_LAUNCH_P(ctx, MB_PROF_GEMM, (gemm_dmma_kernel<AK, BK, 4>), grid, 512, SMEM_BYTES, m, n, k, alpha, A, lda, B, ldb,
+                beta, C, ldc, lower_only ? 1 : 0, tn, nt, a_vec, b_vec, ksplit, kchunk, ws, ws_stride);
+  }
+  if (ksplit > 1) {
+    dim3 rgrid((unsigned)ceil_div64(n, 256), (unsigned)m);
+    MB_LAUNCH(ctx, splitk_reduce_kernel, rgrid, 256, 0, ws, ksplit, ws_stride, m, n, ldc, alpha, beta, C, lower_only ? 1 : 0);
+  }
   return 0;
 }
 

@@ -25,14 +25,33 @@ PAIRS = [
 @pytest.mark.parametrize("n,m,d", [(1, 1, 1), (7, 5, 3), (129, 65, 10), (300, 257, 50), (64, 128, 51),
                                    (1000, 333, 2), (130, 70, 200)])
 @pytest.mark.parametrize("pair", PAIRS, ids=lambda p: p[0].__name__)
-def test_cov_build_matches_oracle(be, pair, n, m, d):
+@pytest.mark.parametrize("variant", [0, 1, 2], ids=["dmma", "dfma", "general"])
+def test_cov_build_matches_oracle(be, variant, pair, n, m, d):
+    """K1 through all three kernels: DMMA tiles + lean sqrt/exp (default), DFMA register tiles, general."""
     rng = np.random.default_rng(n * 1000 + m + d)
     x, y = rng.random((n, d)), rng.random((m, d))
     ls = 0.7 * np.sqrt(d)
-    K = np.asarray(pair[0](ls)(x, y))
+    be.set_option("cov", variant)
+    try:
+        K = np.asarray(pair[0](ls)(x, y))
+    finally:
+        be.set_option("cov", 0)
     Kref = pair[1](ls)(x, y)
     assert K.shape == (n, m)
     np.testing.assert_allclose(K, Kref, rtol=0, atol=2e-13 * max(1.0, np.abs(Kref).max()))
+
+
+@pytest.mark.parametrize("pair", PAIRS[:4], ids=lambda p: p[0].__name__)
+def test_cov_build_dmma_wide_range(be, pair):
+    """The lean exp / sqrt of the DMMA path over many decades of r: short and long length scales, coincident
+    points (sq clamps at 1e-12), far points (k underflows towards 0), odd shapes (scalar-store tail)."""
+    rng = np.random.default_rng(7)
+    x = np.concatenate([rng.random((150, 7)), 40.0 * rng.random((33, 7))])
+    y = np.concatenate([x[:40], rng.random((61, 7)) * 3.0])
+    for ls in (1e-3, 0.05, 1.0, 38.0, 1e4):
+        K = np.asarray(pair[0](ls)(x, y))
+        Kref = pair[1](ls)(x, y)
+        np.testing.assert_allclose(K, Kref, rtol=2e-12, atol=1e-300)
 
 
 def test_ratquad_and_alpha_first_positional(be):
@@ -151,8 +170,8 @@ def test_gemm(be, ta, tb, m, n, k):
     assert rel_err(out, ref) < 1e-13
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("n,r", [(1, 1), (50, 7), (1000, 64), (777, 130), (3000, 257)])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3], ids=["dmma16w", "dfma", "dmma8w", "nosplit"])
+@pytest.mark.parametrize("n,r", [(1, 1), (50, 7), (1000, 64), (777, 130), (3000, 257), (20000, 1500)])
 def test_gram_and_ridge(be, variant, n, r):
     rng = np.random.default_rng(n + r)
     L = rng.standard_normal((n, r)) / np.sqrt(r)
@@ -171,8 +190,9 @@ def test_gram_and_ridge(be, variant, n, r):
         be.set_option("gemm", 0)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("n,r", [(1, 1), (9, 4), (1000, 64), (513, 33), (2000, 1000), (300, 2050), (4000, 5000)])
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("n,r", [(1, 1), (9, 4), (3, 2), (1000, 64), (513, 33), (2000, 1000), (300, 2050), (4000, 5000),
+                                 (5000, 2000), (777, 5000), (20011, 5000), (100, 8192), (64, 9000)])
 def test_loss_grad_hess_transform(be, variant, n, r):
     rng = np.random.default_rng(n * 3 + r)
     L = rng.standard_normal((n, r)) / np.sqrt(r)
@@ -218,10 +238,15 @@ def test_predict_mean(be, nq, m, d, p):
     xq, xu = rng.random((nq, d)), rng.random((m, d))
     w = rng.standard_normal((m, p)) if p > 1 else rng.standard_normal(m)
     cov, covo = C.Matern52(0.8 * np.sqrt(d)), O.Matern52(0.8 * np.sqrt(d))
-    out = be.predict_mean(cov, xq, xu, w, 1.5)
     ref = 1.5 + covo(xq, xu) @ w
-    assert out.shape == ref.shape
-    assert rel_err(out, ref) < 1e-12
+    for variant in (0, 1):
+        be.set_option("cov", variant)
+        try:
+            out = be.predict_mean(cov, xq, xu, w, 1.5)
+        finally:
+            be.set_option("cov", 0)
+        assert out.shape == ref.shape
+        assert rel_err(out, ref) < 1e-12
 
 
 def test_predict_mean_product_kernel(be):

@@ -118,6 +118,90 @@ __global__ void sqrt_kernel(double* out, int iters, double a) {
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+
+#include "../mellon_b200/csrc/mb_math.cuh"
+// lean Matern52 epilogue (mb_math.cuh): sq -> (1 + r + r^2/3) exp(-r), r = sqrt(sq)
+__global__ void lean_matern_kernel(double* out, int iters, double a) {
+  __shared__ double tab[64];
+  { const double t[64] = MB_EXP2_TABLE_INIT; if (threadIdx.x < 64) tab[threadIdx.x] = t[threadIdx.x]; }
+  __syncthreads();
+  double x[4] = {a + threadIdx.x * 1e-3, a * 2, a * 3, a * 4}, s = 0;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      double sq = mbmath::clamp_tiny(x[i]);
+      double r = mbmath::sqrt_pos(sq);
+      double e = mbmath::exp_neg(r, tab);
+      s += fma(fma(r, 1.0 / 3.0, 1.0), r, 1.0) * e;
+      x[i] += 1e-6;
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void libm_matern_kernel(double* out, int iters, double a) {
+  double x[4] = {a + threadIdx.x * 1e-3, a * 2, a * 3, a * 4}, s = 0;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      double sq = fmax(x[i], 0.0);
+      double r = sqrt(sq);
+      double e = exp(-r);
+      s += (r + r * r * (1.0 / 3.0) + 1.0) * e;
+      x[i] += 1e-6;
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// int32 -> f64: cvt.rn.f64.s32 vs the magic-number trick (integer ops + 1 DADD)
+__global__ void i2d_cvt_kernel(double* out, int iters, int a) {
+  int v[8]; double s[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { v[i] = a + threadIdx.x + i; s[i] = 0; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) { s[i] += (double)v[i]; v[i] += 3; }
+  }
+  double t = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) t += s[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = t;
+}
+__global__ void i2d_magic_kernel(double* out, int iters, int a) {
+  int v[8]; double s[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { v[i] = a + threadIdx.x + i; s[i] = 0; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      s[i] += __hiloint2double(0x43300000 ^ 0x00080000, v[i] ^ 0x80000000);  // 2^52+2^51 + (v + 2^31) - ... folded below
+      v[i] += 3;
+    }
+  }
+  double t = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) t += s[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = t;
+}
+// accuracy of the hardware rsqrt seed and of sqrt_pos / exp_neg against libdevice
+__global__ void accuracy_kernel(double* out) {
+  __shared__ double tab[64];
+  { const double t[64] = MB_EXP2_TABLE_INIT; if (threadIdx.x < 64) tab[threadIdx.x] = t[threadIdx.x]; }
+  __syncthreads();
+  double me = 0, ms = 0, mseed = 0;
+  for (int i = 0; i < 20000; i++) {
+    double u = (threadIdx.x * 20000.0 + i + 0.37) / (blockDim.x * 20000.0);
+    double r = u * 60.0;
+    double a = mbmath::exp_neg(r, tab), b = exp(-r);
+    me = fmax(me, fabs(a - b) / b);
+    double s = (1.0 + 3.0 * u) * exp2((double)((i % 200) - 100));
+    double q = mbmath::sqrt_pos(s), q0 = sqrt(s);
+    ms = fmax(ms, fabs(q - q0) / q0);
+    double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+    mseed = fmax(mseed, fabs(y * q0 - 1.0));
+  }
+  out[threadIdx.x * 3 + 0] = me; out[threadIdx.x * 3 + 1] = ms; out[threadIdx.x * 3 + 2] = mseed;
+}
+
 __global__ void copy_kernel(const double2* __restrict__ in, double2* __restrict__ out, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += st) out[i] = in[i];
@@ -189,6 +273,24 @@ int main() {
     printf("exp():  %.2f G evals/s\n", 4.0 * it2 * 512.0 * sm * 2 / ms * 1e-6);
     ms = timeit([&] { sqrt_kernel<<<g, b>>>(out, it2, 0.37); });
     printf("sqrt(): %.2f G evals/s\n", 4.0 * it2 * 512.0 * sm * 2 / ms * 1e-6);
+  }
+
+  {
+    dim3 g(sm * 2), b(512);
+    int it2 = 2000;
+    float ms = timeit([&] { lean_matern_kernel<<<g, b>>>(out, it2, 0.37); });
+    printf("lean Matern52 epilogue: %.2f G evals/s\n", 4.0 * it2 * 512.0 * sm * 2 / ms * 1e-6);
+    ms = timeit([&] { libm_matern_kernel<<<g, b>>>(out, it2, 0.37); });
+    printf("libm Matern52 epilogue: %.2f G evals/s\n", 4.0 * it2 * 512.0 * sm * 2 / ms * 1e-6);
+    ms = timeit([&] { i2d_cvt_kernel<<<g, b>>>(out, it2, 5); });
+    printf("cvt.f64.s32 + dadd: %.2f G/s\n", 8.0 * it2 * 512.0 * sm * 2 / ms * 1e-6);
+    ms = timeit([&] { i2d_magic_kernel<<<g, b>>>(out, it2, 5); });
+    printf("magic i2d + dadd:   %.2f G/s\n", 8.0 * it2 * 512.0 * sm * 2 / ms * 1e-6);
+    accuracy_kernel<<<1, 256>>>(out); CK(cudaDeviceSynchronize());
+    double h[768]; CK(cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost));
+    double me = 0, msq = 0, mseed = 0;
+    for (int i = 0; i < 256; i++) { me = fmax(me, h[3*i]); msq = fmax(msq, h[3*i+1]); mseed = fmax(mseed, h[3*i+2]); }
+    printf("accuracy on device: exp_neg max rel %.3e, sqrt_pos max rel %.3e, rsqrt seed max rel %.3e\n", me, msq, mseed);
   }
   {
     size_t bytes = (size_t)8 << 30;  // 8 GiB each
