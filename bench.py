@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=20_000, help="cells of the workload the CPU baseline times")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region (A/B only)")
     return ap.parse_args()
 
 
@@ -243,7 +244,7 @@ def run_b200(args):
     dist.barrier()
     be.sync()
     launches0 = be.launch_count()
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         sampler.start()
     be.timer_start(0)
     nfev = []
@@ -303,7 +304,7 @@ def run_b200(args):
     except (OSError, ValueError):
         pass
     roofline = {
-        "kernel": "cov_tile_kernel (K1: fused pairwise distance + covariance, K_NM build)",
+        "kernel": "cov_mma_kernel (K1: fused pairwise distance + covariance, K_NM build; FP64-issue bound, see DESIGN.md)",
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
         "frac": achieved / hbm_peak if hbm_peak else None, "traffic": traffic, "peak_source": peak_src,
         "launches": n_cov, "avg_launch_ms": ms_cov / max(n_cov, 1),

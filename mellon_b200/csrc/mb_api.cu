@@ -60,6 +60,7 @@ extern "C" int mb_ctx_destroy(mb_ctx* c) {
   if (c->scratch) cudaFree(c->scratch);
   if (c->flush_buf) cudaFree(c->flush_buf);
   if (c->gemm_ws) cudaFree(c->gemm_ws);
+  if (c->trsm_ws) cudaFree(c->trsm_ws);
   if (c->pinned) cudaFreeHost(c->pinned);
   prof_resolve(c);
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
@@ -171,6 +172,7 @@ extern "C" int mb_set_option(mb_ctx* c, const char* key, int value) {
   MB_CHECK(c && key, "mb_set_option: null");
   if (!strcmp(key, "gemm")) c->opt_gemm = value;
   else if (!strcmp(key, "cov")) c->opt_cov = value;
+  else if (!strcmp(key, "trsm")) c->opt_trsm = value;
   else if (!strcmp(key, "lossgrad")) c->opt_lossgrad = value;
   else MB_CHECK(false, "mb_set_option: unknown key %s", key);
   return 0;

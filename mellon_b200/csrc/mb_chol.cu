@@ -90,6 +90,51 @@ int trsm_rec(mb_ctx* ctx, const double* Lp, int64_t ldl, int64_t c0, int64_t w, 
   return trsm_rec(ctx, Lp, ldl, c0 + w1, w - w1, X, ldx, nrows);
 }
 
+
+// ---- inverse of the 128-wide diagonal blocks of a lower-triangular matrix -----------------------
+// One CTA per block, thread c solves T x = e_c by forward substitution (column c of T^-1); T is
+// staged in shared memory.  Output: dense 128 x 128 blocks (zero above the diagonal and beyond w).
+constexpr int IB = 128;
+__global__ void __launch_bounds__(IB)
+tri_inv_blocks_kernel(const double* __restrict__ L, int64_t ldl, int64_t m, double* __restrict__ inv) {
+  extern __shared__ double Tsh[];  // IB x (IB + 1)
+  const int64_t j0 = (int64_t)blockIdx.x * IB;
+  const int w = (int)min((int64_t)IB, m - j0);
+  const int c = threadIdx.x;
+  for (int e = c; e < IB * IB; e += IB) {
+    const int r = e / IB, k = e % IB;
+    Tsh[r * (IB + 1) + k] = (r < w && k < w && k <= r) ? L[(j0 + r) * ldl + j0 + k] : 0.0;
+  }
+  __syncthreads();
+  double* out = inv + (int64_t)blockIdx.x * IB * IB;
+  // column c of the inverse lives in x[] = out[:, c]; rows above c are zero
+  for (int r = 0; r < IB; r++) {
+    double v = 0.0;
+    if (c < w && r < w && r >= c) {
+      double s = (r == c) ? 1.0 : 0.0;
+      for (int k = c; k < r; k++) s = fma(-Tsh[r * (IB + 1) + k], out[(int64_t)k * IB + c], s);
+      v = s / Tsh[r * (IB + 1) + r];
+    }
+    out[(int64_t)r * IB + c] = v;  // each thread re-reads only its own column: no barrier needed
+  }
+}
+
+// X[:, c0:c0+w] <- X[:, c0:c0+w] Lp[c0:c0+w, c0:c0+w]^-T with GEMM leaves on the inverted diagonal blocks
+int trsm_inv_rec(mb_ctx* ctx, const double* Lp, int64_t ldl, const double* inv, int64_t c0, int64_t w, double* X,
+                 int64_t ldx, int64_t nrows) {
+  if (w <= 0) return 0;
+  if (w <= IB) {
+    // in place: a CTA consumes its whole 128 x w input tile before it stores the same tile
+    const double* Tinv = inv + (c0 / IB) * IB * IB;
+    return mb_gemm_raw(ctx, false, false, nrows, w, w, 1.0, X + c0, ldx, Tinv, IB, 0.0, X + c0, ldx, false);
+  }
+  const int64_t w1 = ((w / 2 + IB - 1) / IB) * IB;
+  MB_TRY(trsm_inv_rec(ctx, Lp, ldl, inv, c0, w1, X, ldx, nrows));
+  MB_TRY(mb_gemm_raw(ctx, false, false, nrows, w - w1, w1, -1.0, X + c0, ldx, Lp + (c0 + w1) * ldl + c0, ldl, 1.0,
+                     X + c0 + w1, ldx, false));
+  return trsm_inv_rec(ctx, Lp, ldl, inv, c0 + w1, w - w1, X, ldx, nrows);
+}
+
 int potrf_rec(mb_ctx* ctx, double* A, int64_t lda, int64_t off, int64_t n, int* info) {
   if (n <= 0) return 0;
   double* D = A + off * lda + off;
@@ -240,7 +285,26 @@ trsv_kernel(const double* __restrict__ L, int64_t ldl, int m, double* __restrict
 int mb_trsm_right_lt_raw(mb_ctx* ctx, const double* Lp, int64_t ldl, int64_t m, double* X, int64_t ldx,
                          int64_t nrows) {
   if (nrows <= 0 || m <= 0) return 0;
-  return trsm_rec(ctx, Lp, ldl, 0, m, X, ldx, nrows);
+  if (ctx->opt_trsm == 1 || nrows < 4 * IB) return trsm_rec(ctx, Lp, ldl, 0, m, X, ldx, nrows);
+  // tall right-hand sides: every flop in the DMMA GEMM (diagonal blocks applied as explicit 128 x 128 inverses)
+  const int64_t nb = ceil_div64(m, IB);
+  const size_t need = (size_t)nb * IB * IB * sizeof(double);
+  if (need > ctx->trsm_ws_bytes) {
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->trsm_ws) MB_CUDA(cudaFree(ctx->trsm_ws));
+    ctx->trsm_ws = nullptr;
+    ctx->trsm_ws_bytes = 0;
+    MB_CUDA(cudaMalloc(&ctx->trsm_ws, need));
+    ctx->trsm_ws_bytes = need;
+  }
+  static bool configured = false;
+  const size_t smem = (size_t)IB * (IB + 1) * sizeof(double);
+  if (!configured) {
+    MB_CUDA(cudaFuncSetAttribute(tri_inv_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  MB_LAUNCH(ctx, tri_inv_blocks_kernel, (int)nb, IB, smem, Lp, ldl, m, ctx->trsm_ws);
+  return trsm_inv_rec(ctx, Lp, ldl, ctx->trsm_ws, 0, m, X, ldx, nrows);
 }
 
 int mb_potrf_raw(mb_ctx* ctx, double* A, int64_t n, int64_t lda, int* info_dev) {

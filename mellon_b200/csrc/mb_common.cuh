@@ -42,6 +42,8 @@ struct mb_ctx {
   size_t pinned_bytes = 0;
   double* flush_buf = nullptr;
   size_t flush_bytes = 0;
+  double* trsm_ws = nullptr;           // inverted 128 x 128 diagonal blocks of the TRSM
+  size_t trsm_ws_bytes = 0;
   double* gemm_ws = nullptr;           // split-k partial tiles (own buffer: GEMMs run inside scratch users)
   size_t gemm_ws_bytes = 0;
   // NCCL
@@ -50,6 +52,7 @@ struct mb_ctx {
   // options
   int opt_gemm = 0;      // 0 = DMMA tiles (default), 1 = DFMA register tiles
   int opt_cov = 0;       // 0 = DMMA tile kernel (exp-family leaf) else 1; 1 = DFMA register-tile kernel; 2 = general kernel
+  int opt_trsm = 0;      // 0 = GEMM leaves on inverted 128-blocks (tall X), 1 = 32-wide substitution leaves
   int opt_lossgrad = 0;  // 0 = TMA-ring streaming single pass, 1 = two-pass, 2 = register-fused single pass
   // per-kernel-class stopwatch
   bool prof_on = false;

@@ -772,7 +772,7 @@ int prepare(mb_ctx* ctx, const mb_kprog* kp, const mb_mat* x, const mb_mat* y, P
     const Leaf& lf = plan->prog.leaves[0];
     const int d0 = lf.all_dims ? (int)x->cols : (int)lf.dims.size();
     const double sc = mma_scale(lf);
-    if (sc > 0.0 && (size_t)(MBM + 2 * MBN) * ldp_mma(d0) * sizeof(double) <= 100 * 1024) {
+    if (sc > 0.0 && (size_t)(MBM + 2 * MBN) * ldp_mma(d0) * sizeof(double) <= 200 * 1024) {
       plan->mma = true;
       plan->eps_scaled = 1e-12 * sc * sc;
       scale = sc;
@@ -909,7 +909,7 @@ int launch_mma(mb_ctx* ctx, const Plan& plan, int64_t n, int64_t m, double* out,
     static bool cfg = false;                                                                                 \
     if (!cfg) {                                                                                              \
       MB_CUDA(cudaFuncSetAttribute(cov_mma_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                   100 * 1024));                                                             \
+                                   200 * 1024));                                                             \
       cfg = true;                                                                                            \
     }                                                                                                        \
     MB_LAUNCH_P(ctx, prof_cls, (cov_mma_kernel<K, MODE>), grid, MNT, smem, xo.p, xo.norm, n, yo.p, yo.norm, m, ldp, \

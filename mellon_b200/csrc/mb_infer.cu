@@ -252,26 +252,27 @@ __device__ __forceinline__ void s_bulk_g2s(void* dst, const void* src, uint32_t 
                : "memory");
 }
 
-constexpr int ST = 512, SNW = ST / 32, SMAX_RB = 8, SMAX_NS = 8;
-constexpr int ST_ALL = ST + 64;  // 16 compute warps + 1 scalar warp + 1 producer warp
+constexpr int ST = 448, SNW = ST / 32, SMAX_RB = 8, SMAX_NS = 8;  // 14 compute warps
+constexpr int ST_ALL = ST + 64;  // + 1 scalar warp + 1 producer warp = 512 threads (128 registers each)
+constexpr int SRED = 16;          // partial-sum slots per row (slots >= SNW stay zero)
 
 __device__ __forceinline__ void s_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(s_u32(bar)) : "memory");
 }
 
 // Warp roles (no __syncthreads in the row loop; everything is mbarrier hand-offs):
-//   producer warp : waits for a ring stage to be released by the 16 compute warps, re-arms its
+//   producer warp : waits for a ring stage to be released by the 14 compute warps, re-arms its
 //                   `full` barrier and issues the bulk copy of the next slab into it;
-//   compute warps : slab k   -> partial row dots (columns c = 2t + 1024q of thread t), warp-reduced,
+//   compute warps : slab k   -> partial row dots (columns c = 2t + 896q of thread t), warp-reduced,
 //                               posted to red[k&1] and signalled on dot_ready[k&1];
 //                   slab k-1 -> gradient / Hessian accumulation with the weights the scalar warp
 //                               published on w_ready[(k-1)&1] one iteration earlier, then the stage is
 //                               released on empty[];
-//   scalar warp   : sums the 16 warp partials of each row in a fixed order, f = mu + dot,
+//   scalar warp   : sums the 14 warp partials of each row in a fixed order, f = mu + dot,
 //                   A = exp(f + V), weight = A - 1 (or A), loss partial sum; publishes wsh[k&1].
 // The serial exp chain of the scalar warp therefore overlaps the compute warps' next slab instead
 // of stalling them (the single-barrier version sat at 2700 clk per 40 KB row, 4.4 TB/s).
-template <int CP, bool SQ>
+template <int CP, bool SQ, bool HOLD>
 __global__ void __launch_bounds__(ST_ALL, 1)
 stream_rows_kernel(const double* __restrict__ L, int64_t n, int r, const double* __restrict__ z, double mu,
                    const double* __restrict__ V, int64_t rows_per_cta, int rb, int ns,
@@ -279,7 +280,7 @@ stream_rows_kernel(const double* __restrict__ L, int64_t n, int r, const double*
   extern __shared__ __align__(128) unsigned char stream_smem[];
   double* ring = reinterpret_cast<double*>(stream_smem);
   __shared__ __align__(8) uint64_t full[SMAX_NS], empty[SMAX_NS], dot_ready[2], w_ready[2];
-  __shared__ double red[2][SMAX_RB][SNW];
+  __shared__ double red[2][SMAX_RB][SRED];
   __shared__ double wsh[2][SMAX_RB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t i0 = (int64_t)blockIdx.x * rows_per_cta;
@@ -287,6 +288,7 @@ stream_rows_kernel(const double* __restrict__ L, int64_t n, int r, const double*
   const int64_t nslab = (i1 > i0) ? (i1 - i0 + rb - 1) / rb : 0;
   const size_t stage_doubles = (size_t)rb * r;
 
+  for (int e = tid; e < 2 * SMAX_RB * SRED; e += ST_ALL) (&red[0][0][0])[e] = 0.0;
   if (tid == 0) {
     for (int s = 0; s < ns; s++) {
       s_mbar_init(&full[s], 1);
@@ -357,51 +359,97 @@ stream_rows_kernel(const double* __restrict__ L, int64_t n, int r, const double*
     zr[q].y = (c + 1 < r) ? z[c + 1] : 0.0;
     g[q] = make_double2(0.0, 0.0);
   }
-  for (int64_t k = 0; k <= nslab; k++) {
-    const int pb = (int)(k & 1);
-    if (k < nslab) {
-      const int rows_k = (int)min((int64_t)rb, i1 - (i0 + k * rb));
-      s_mbar_wait(&full[k % ns], (uint32_t)((k / ns) & 1));
-      const double* slab = ring + (size_t)(k % ns) * stage_doubles;
-      for (int rr = 0; rr < rows_k; rr++) {
-        const double* row = slab + (size_t)rr * r;
+  if (HOLD) {
+    // one row per slab (rb == 1): the row is read from shared memory ONCE, its stage is released at
+    // once, and the copy held in registers serves the gradient one iteration later
+    double2 vcur[CP], vprev[CP];
+#pragma unroll
+    for (int q = 0; q < CP; q++) vprev[q] = make_double2(0.0, 0.0);
+    for (int64_t k = 0; k <= nslab; k++) {
+      const int pb = (int)(k & 1);
+      if (k < nslab) {
+        s_mbar_wait(&full[k % ns], (uint32_t)((k / ns) & 1));
+        const double* row = ring + (size_t)(k % ns) * stage_doubles;
+#pragma unroll
+        for (int q = 0; q < CP; q++) {
+          const int c = 2 * tid + 2 * ST * q;
+          vcur[q] = (c < r) ? *reinterpret_cast<const double2*>(row + c) : make_double2(0.0, 0.0);
+        }
+        __syncwarp();
+        if (lane == 0) s_mbar_arrive(&empty[k % ns]);
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int q = 0; q < CP; q++) {
-          const int c = 2 * tid + 2 * ST * q;
-          if (c < r) {
-            const double2 v = *reinterpret_cast<const double2*>(row + c);
-            s0 = fma(v.x, zr[q].x, s0);
-            s1 = fma(v.y, zr[q].y, s1);
-          }
+          s0 = fma(vcur[q].x, zr[q].x, s0);
+          s1 = fma(vcur[q].y, zr[q].y, s1);
         }
         const double s = warp_sum(s0 + s1);
-        if (lane == 0) red[pb][rr][warp] = s;
-      }
-      __syncwarp();
-      if (lane == 0) s_mbar_arrive(&dot_ready[pb]);
-    }
-    if (k >= 1) {
-      const int64_t kp = k - 1;
-      const int rows_p = (int)min((int64_t)rb, i1 - (i0 + kp * rb));
-      s_mbar_wait(&w_ready[pb ^ 1], (uint32_t)((kp >> 1) & 1));
-      const double* slab = ring + (size_t)(kp % ns) * stage_doubles;
-      for (int rr = 0; rr < rows_p; rr++) {
-        const double wgt = wsh[pb ^ 1][rr];
-        const double* row = slab + (size_t)rr * r;
-#pragma unroll
-        for (int q = 0; q < CP; q++) {
-          const int c = 2 * tid + 2 * ST * q;
-          if (c < r) {
-            double2 v = *reinterpret_cast<const double2*>(row + c);
-            if (SQ) { v.x *= v.x; v.y *= v.y; }
-            g[q].x = fma(wgt, v.x, g[q].x);
-            g[q].y = fma(wgt, v.y, g[q].y);
-          }
+        if (lane == 0) {
+          red[pb][0][warp] = s;
+          s_mbar_arrive(&dot_ready[pb]);
         }
       }
-      __syncwarp();
-      if (lane == 0) s_mbar_arrive(&empty[kp % ns]);
+      if (k >= 1) {
+        s_mbar_wait(&w_ready[pb ^ 1], (uint32_t)(((k - 1) >> 1) & 1));
+        const double wgt = wsh[pb ^ 1][0];
+#pragma unroll
+        for (int q = 0; q < CP; q++) {
+          double2 v = vprev[q];
+          if (SQ) { v.x *= v.x; v.y *= v.y; }
+          g[q].x = fma(wgt, v.x, g[q].x);
+          g[q].y = fma(wgt, v.y, g[q].y);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < CP; q++) vprev[q] = vcur[q];
+    }
+  } else {
+    for (int64_t k = 0; k <= nslab; k++) {
+      const int pb = (int)(k & 1);
+      if (k < nslab) {
+        const int rows_k = (int)min((int64_t)rb, i1 - (i0 + k * rb));
+        s_mbar_wait(&full[k % ns], (uint32_t)((k / ns) & 1));
+        const double* slab = ring + (size_t)(k % ns) * stage_doubles;
+        for (int rr = 0; rr < rows_k; rr++) {
+          const double* row = slab + (size_t)rr * r;
+          double s0 = 0.0, s1 = 0.0;
+  #pragma unroll
+          for (int q = 0; q < CP; q++) {
+            const int c = 2 * tid + 2 * ST * q;
+            if (c < r) {
+              const double2 v = *reinterpret_cast<const double2*>(row + c);
+              s0 = fma(v.x, zr[q].x, s0);
+              s1 = fma(v.y, zr[q].y, s1);
+            }
+          }
+          const double s = warp_sum(s0 + s1);
+          if (lane == 0) red[pb][rr][warp] = s;
+        }
+        __syncwarp();
+        if (lane == 0) s_mbar_arrive(&dot_ready[pb]);
+      }
+      if (k >= 1) {
+        const int64_t kp = k - 1;
+        const int rows_p = (int)min((int64_t)rb, i1 - (i0 + kp * rb));
+        s_mbar_wait(&w_ready[pb ^ 1], (uint32_t)((kp >> 1) & 1));
+        const double* slab = ring + (size_t)(kp % ns) * stage_doubles;
+        for (int rr = 0; rr < rows_p; rr++) {
+          const double wgt = wsh[pb ^ 1][rr];
+          const double* row = slab + (size_t)rr * r;
+  #pragma unroll
+          for (int q = 0; q < CP; q++) {
+            const int c = 2 * tid + 2 * ST * q;
+            if (c < r) {
+              double2 v = *reinterpret_cast<const double2*>(row + c);
+              if (SQ) { v.x *= v.x; v.y *= v.y; }
+              g[q].x = fma(wgt, v.x, g[q].x);
+              g[q].y = fma(wgt, v.y, g[q].y);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) s_mbar_arrive(&empty[kp % ns]);
+      }
     }
   }
   double* p = partial + (int64_t)blockIdx.x * r;
@@ -520,21 +568,30 @@ int launch_stream(mb_ctx* ctx, const mb_mat* L, const double* zdev, double mu, c
   const int grid = (int)ceil_div64(n, rows_per_cta);
   const size_t smem = (size_t)ns * stage;
   const int cp = (int)ceil_div64(r, 2 * ST);
+  const bool hold = (rb == 1 && cp <= 6);  // row copy in registers: 4 * cp more registers
 #define MB_STREAM(CPV)                                                                                      \
   case CPV: {                                                                                               \
     static bool cfg = false;                                                                                \
     if (!cfg) {                                                                                             \
-      MB_CUDA(cudaFuncSetAttribute(stream_rows_kernel<CPV, SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      MB_CUDA(cudaFuncSetAttribute(stream_rows_kernel<CPV, SQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   (int)budget));                                                           \
+      MB_CUDA(cudaFuncSetAttribute(stream_rows_kernel<CPV, SQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    (int)budget));                                                           \
       cfg = true;                                                                                           \
     }                                                                                                       \
     if (ctx->prof_on) ctx->prof_work[MB_PROF_LOSSGRAD] += 8.0 * ((double)n * r + (double)n);                \
-    MB_LAUNCH_P(ctx, MB_PROF_LOSSGRAD, (stream_rows_kernel<CPV, SQ>), grid, ST_ALL, smem, L->p, n, r, zdev, mu, V, \
-                rows_per_cta, rb, ns, pb->partial, pb->lpartial);                                           \
+    if (hold) {                                                                                             \
+      MB_LAUNCH_P(ctx, MB_PROF_LOSSGRAD, (stream_rows_kernel<CPV, SQ, true>), grid, ST_ALL, smem, L->p, n, r, zdev, mu, \
+                  V, rows_per_cta, rb, ns, pb->partial, pb->lpartial);                                      \
+    } else {                                                                                                \
+      MB_LAUNCH_P(ctx, MB_PROF_LOSSGRAD, (stream_rows_kernel<CPV, SQ, false>), grid, ST_ALL, smem, L->p, n, r, zdev, mu, \
+                  V, rows_per_cta, rb, ns, pb->partial, pb->lpartial);                                      \
+    }                                                                                                       \
     break;                                                                                                  \
   }
   switch (cp) {
     MB_STREAM(1) MB_STREAM(2) MB_STREAM(3) MB_STREAM(4) MB_STREAM(5) MB_STREAM(6) MB_STREAM(7) MB_STREAM(8)
+    MB_STREAM(9) MB_STREAM(10)
     default: return 0;
   }
 #undef MB_STREAM

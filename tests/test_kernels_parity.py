@@ -41,17 +41,32 @@ def test_cov_build_matches_oracle(be, variant, pair, n, m, d):
     np.testing.assert_allclose(K, Kref, rtol=0, atol=2e-13 * max(1.0, np.abs(Kref).max()))
 
 
+SCALE2 = {"Matern32": 3.0, "Matern52": 5.0, "ExpQuad": 0.5, "Exponential": 0.25}  # (r / (dist / ls))^2
+
+
 @pytest.mark.parametrize("pair", PAIRS[:4], ids=lambda p: p[0].__name__)
 def test_cov_build_dmma_wide_range(be, pair):
-    """The lean exp / sqrt of the DMMA path over many decades of r: short and long length scales, coincident
-    points (sq clamps at 1e-12), far points (k underflows towards 0), odd shapes (scalar-store tail)."""
+    """The lean exp / sqrt of the DMMA path over many decades of r: short and long length scales, near and
+    far points (k underflows towards 0), odd shapes (scalar-store tail).
+
+    Tolerance: the expansion xx - 2xy + yy carries ~eps (|x|^2 + |y|^2) of absolute noise in the squared
+    distance on BOTH sides (reference and kernel round it differently), which a kernel value turns into a
+    relative error of eps c^2 (|x|^2 + |y|^2) |dlog k / d(r^2)| with |dlog k / d(r^2)| <= max(1, 1 / (2 r)).
+    Allow 64x that plus 2e-12."""
     rng = np.random.default_rng(7)
-    x = np.concatenate([rng.random((150, 7)), 40.0 * rng.random((33, 7))])
-    y = np.concatenate([x[:40], rng.random((61, 7)) * 3.0])
-    for ls in (1e-3, 0.05, 1.0, 38.0, 1e4):
+    x = np.concatenate([rng.random((150, 7)), 3.0 + rng.random((33, 7))])
+    y = np.concatenate([x[:40] + 0.05, rng.random((61, 7)) * 3.0])
+    sqn = (x * x).sum(1)[:, None] + (y * y).sum(1)[None, :]
+    dist = O.distance(x, y)
+    eps = np.finfo(float).eps
+    for ls in (0.05, 1.0, 38.0, 1e4):
         K = np.asarray(pair[0](ls)(x, y))
         Kref = pair[1](ls)(x, y)
-        np.testing.assert_allclose(K, Kref, rtol=2e-12, atol=1e-300)
+        c2 = SCALE2[pair[0].__name__] / ls ** 2
+        r = np.sqrt(c2) * dist
+        tol = 2e-12 + 64 * eps * c2 * sqn * np.maximum(1.0, 0.5 / r)
+        err = np.abs(K - Kref) / np.maximum(np.abs(Kref), 1e-300)
+        assert np.all((err <= tol) | (np.abs(K - Kref) < 1e-300)), float(np.max(err / tol))
 
 
 def test_ratquad_and_alpha_first_positional(be):
@@ -137,12 +152,18 @@ def test_potrf_reports_non_positive_definite(be):
     assert 1 <= info <= 41
 
 
-@pytest.mark.parametrize("n,m", [(1, 1), (10, 33), (500, 100), (131, 257)])
-def test_trsm_right(be, n, m):
+@pytest.mark.parametrize("variant", [0, 1], ids=["inv128-gemm-leaves", "substitution-leaves"])
+@pytest.mark.parametrize("n,m", [(1, 1), (10, 33), (500, 100), (131, 257), (513, 1), (700, 128), (1000, 129),
+                                 (2000, 300), (3000, 1000)])
+def test_trsm_right(be, variant, n, m):
     rng = np.random.default_rng(n + m)
     Lp = np.linalg.cholesky(_spd(m, m, 1e4))
     X = rng.standard_normal((n, m))
-    out = be.trsm_right_lt(be.upload(Lp), be.upload(X.copy())).numpy()
+    be.set_option("trsm", variant)
+    try:
+        out = be.trsm_right_lt(be.upload(Lp), be.upload(X.copy())).numpy()
+    finally:
+        be.set_option("trsm", 0)
     ref = solve_triangular(Lp, X.T, lower=True).T
     assert rel_err(out, ref) < 1e-11
 

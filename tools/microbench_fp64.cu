@@ -101,6 +101,90 @@ __global__ void mixed_kernel(double* out, int iters, double a, double b) {
   for (int i = 0; i < NF; i++) s += f[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+
+// GEMM-shaped inner loops: fragments come from shared memory with rotating registers, 32x32 warp tile.
+//   SHAPE 0: m8n8k4   16 MMAs + 8 LDS.64 per k4 step
+//   SHAPE 1: m16n8k8   8 MMAs + 16 LDS.64 per k8 step
+//   SHAPE 2: m16n8k16  8 MMAs + 32 LDS.64 per k16 step
+// SYNC_EVERY > 0 adds a __syncthreads every SYNC_EVERY k16-equivalents (the k-tile barrier of the GEMM).
+template <int SHAPE, int SYNC_EVERY>
+__global__ void __launch_bounds__(512, 1) gemm_loop_kernel(double* out, int iters) {
+  __shared__ double sa[128 * 20], sb[128 * 20];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < 128 * 20; e += blockDim.x) { sa[e] = 1e-3 * e; sb[e] = 2e-3 * e; }
+  __syncthreads();
+  const int lr = lane >> 2, lk = lane & 3;
+  const double* pa = sa + ((warp >> 2) * 32 + lr) * 20 + lk;
+  const double* pb = sb + ((warp & 3) * 32 + lr) * 20 + lk;
+  double acc[4][4][2];   // m8n8k4 view
+  double acc4[2][4][4];  // m16n8kX view
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc4[i][j][0] = acc4[i][j][1] = acc4[i][j][2] = acc4[i][j][3] = 0.0;
+  for (int it = 0; it < iters; it++) {
+    if (SHAPE == 0) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ks++) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) af[i] = pa[i * 160 + ks * 4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) bf[j] = pb[j * 160 + ks * 4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+    } else if (SHAPE == 1) {
+#pragma unroll
+      for (int ks = 0; ks < 2; ks++) {
+        double af[2][4], bf[4][2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          af[i][0] = pa[(i * 16) * 20 + ks * 8];      af[i][1] = pa[(i * 16 + 8) * 20 + ks * 8];
+          af[i][2] = pa[(i * 16) * 20 + ks * 8 + 4];  af[i][3] = pa[(i * 16 + 8) * 20 + ks * 8 + 4];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) { bf[j][0] = pb[j * 160 + ks * 8]; bf[j][1] = pb[j * 160 + ks * 8 + 4]; }
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) dmma1688(acc4[i][j], af[i], bf[j]);
+      }
+    } else {
+      double af[2][8], bf[4][4];
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) { af[i][2 * q] = pa[(i * 16) * 20 + q * 4]; af[i][2 * q + 1] = pa[(i * 16 + 8) * 20 + q * 4]; }
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) bf[j][q] = pb[j * 160 + q * 4];
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma16816(acc4[i][j], af[i], bf[j]);
+    }
+    if (SYNC_EVERY > 0 && (it % SYNC_EVERY) == SYNC_EVERY - 1) __syncthreads();
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) s += acc[i][j][0] + acc[i][j][1];
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) s += acc4[i][j][0] + acc4[i][j][1] + acc4[i][j][2] + acc4[i][j][3];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // exp / sqrt throughput
 __global__ void exp_kernel(double* out, int iters, double a) {
   double x[4] = {a + threadIdx.x * 1e-3, a * 2, a * 3, a * 4}, s = 0;
@@ -235,7 +319,7 @@ int main() {
   printf("device %s, %d SMs, cc %d.%d\n", p.name, sm, p.major, p.minor);
   double* out; CK(cudaMalloc(&out, sizeof(double) * sm * 8 * 1024));
   const int iters = 20000;
-  for (int warps : {4, 8, 16, 32}) {
+  for (int warps : {4, 8, 16}) {
     int threads = warps * 32;
     dim3 g(sm), b(threads);
     float ms = timeit([&] { dfma_kernel<16><<<g, b>>>(out, iters, 1.0000001, 1e-9); });
@@ -265,6 +349,26 @@ int main() {
     printf("ONLY  8 dmma884 / iter (16 warps): %.3f ms -> %.2f TF\n", ms, fl_m / ms * 1e-9);
     ms = timeit([&] { mixed_kernel<0, 32><<<g, b>>>(out, iters, 1.0000001, 1e-9); });
     printf("ONLY  32 dfma / iter (16 warps): %.3f ms -> %.2f TF\n", ms, fl_f / ms * 1e-9);
+  }
+
+  {
+    dim3 g(sm), b(512);
+    const int it3 = 20000;
+    const double fl = 2.0 * 32 * 32 * 16 * (double)it3 * 16 * sm;  // per iteration each warp does a 32x32x16 product
+    float ms = timeit([&] { gemm_loop_kernel<0, 0><<<g, b>>>(out, it3); });
+    printf("GEMM-loop m8n8k4   smem frags, no sync : %.2f TF\n", fl / ms * 1e-9);
+    ms = timeit([&] { gemm_loop_kernel<0, 1><<<g, b>>>(out, it3); });
+    printf("GEMM-loop m8n8k4   smem frags, sync/k16: %.2f TF\n", fl / ms * 1e-9);
+    ms = timeit([&] { gemm_loop_kernel<0, 2><<<g, b>>>(out, it3); });
+    printf("GEMM-loop m8n8k4   smem frags, sync/k32: %.2f TF\n", fl / ms * 1e-9);
+    ms = timeit([&] { gemm_loop_kernel<1, 0><<<g, b>>>(out, it3); });
+    printf("GEMM-loop m16n8k8  smem frags, no sync : %.2f TF\n", fl / ms * 1e-9);
+    ms = timeit([&] { gemm_loop_kernel<1, 1><<<g, b>>>(out, it3); });
+    printf("GEMM-loop m16n8k8  smem frags, sync/k16: %.2f TF\n", fl / ms * 1e-9);
+    ms = timeit([&] { gemm_loop_kernel<2, 0><<<g, b>>>(out, it3); });
+    printf("GEMM-loop m16n8k16 smem frags, no sync : %.2f TF\n", fl / ms * 1e-9);
+    ms = timeit([&] { gemm_loop_kernel<2, 1><<<g, b>>>(out, it3); });
+    printf("GEMM-loop m16n8k16 smem frags, sync/k16: %.2f TF\n", fl / ms * 1e-9);
   }
   {
     dim3 g(sm * 2), b(512);
