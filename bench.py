@@ -323,9 +323,20 @@ def run_b200(args):
     }
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    parity = None
+    if not args.no_cpu_baseline and world == 1:
         xs, lms, nns, ns = cpu_sample(args, x, lm, nn)
         dt, fit, tm = cpu_fit(xs, lms, nns, args.cov)
+        # parity on the very sample the CPU arm just fitted: the same cells through the CUDA path
+        dens_s = mb.DensityEstimator(cov_func_curry=cov_curry, landmarks=lms, nn_distances=nns,
+                                     check_rank=False).fit_predict(xs)
+        ref_s = np.asarray(fit.log_density_x)
+        parity = {
+            "sample": f"first {ns} cells, all {args.landmarks} landmarks: CUDA fit_predict vs the CPU oracle's",
+            "max_rel_err_log_density": float(np.max(np.abs(dens_s - ref_s) / np.abs(ref_s))),
+            "max_abs_err_over_max_abs": float(np.max(np.abs(dens_s - ref_s)) / np.max(np.abs(ref_s))),
+            "tolerance": 1e-5,
+        }
         cpu_baseline = {
             "value": ns / dt, "unit": UNIT, "cores": threads_used(), "kind": "port",
             "sample": f"first {ns} cells of the workload (all {args.landmarks} landmarks, their nn_distances taken "
@@ -339,7 +350,7 @@ def run_b200(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
-        "cpu_baseline": cpu_baseline, "lbfgsb": {"nfev_per_step": nfev, "nit_last": nit},
+        "cpu_baseline": cpu_baseline, "parity": parity, "lbfgsb": {"nfev_per_step": nfev, "nit_last": nit},
         "log_density_checksum": checksum,
     }
     print(json.dumps(line))

@@ -280,15 +280,67 @@ trsv_kernel(const double* __restrict__ L, int64_t ldl, int m, double* __restrict
   for (int i = tid; i < m; i += blockDim.x) B[(int64_t)i * nrhs + col] = xs[i];
 }
 
-}  // namespace
 
-int mb_trsm_right_lt_raw(mb_ctx* ctx, const double* Lp, int64_t ldl, int64_t m, double* X, int64_t ldx,
-                         int64_t nrows) {
-  if (nrows <= 0 || m <= 0) return 0;
-  if (ctx->opt_trsm == 1 || nrows < 4 * IB) return trsm_rec(ctx, Lp, ldl, 0, m, X, ldx, nrows);
-  // tall right-hand sides: every flop in the DMMA GEMM (diagonal blocks applied as explicit 128 x 128 inverses)
-  const int64_t nb = ceil_div64(m, IB);
-  const size_t need = (size_t)nb * IB * IB * sizeof(double);
+// ---- leaf: Cholesky of one (w <= 128) diagonal block in shared memory, one thread per row ----
+__global__ void __launch_bounds__(IB)
+potrf_leaf128_kernel(double* __restrict__ A, int64_t lda, int w, int64_t global_off, int* info) {
+  extern __shared__ double Ssh[];  // IB x (IB + 1)
+  const int i = threadIdx.x;
+  constexpr int LDS_ = IB + 1;
+  for (int e = i; e < IB * IB; e += IB) {
+    const int r = e / IB, k = e % IB;
+    Ssh[r * LDS_ + k] = (r < w && k <= r) ? A[(int64_t)r * lda + k] : 0.0;
+  }
+  __syncthreads();
+  for (int j = 0; j < w; j++) {
+    double d = Ssh[j * LDS_ + j];
+    if (!(d > 0.0)) {
+      if (i == 0) atomicCAS(info, 0, (int)(global_off + j + 1));
+      d = nan("");
+    }
+    d = sqrt(d);
+    __syncthreads();
+    double lij = 0.0;
+    if (i == j) Ssh[j * LDS_ + j] = d;
+    if (i > j && i < w) {
+      lij = Ssh[i * LDS_ + j] / d;
+      Ssh[i * LDS_ + j] = lij;
+    }
+    __syncthreads();
+    if (i > j && i < w) {
+      double* row = Ssh + i * LDS_;
+      for (int k = j + 1; k <= i; k++) row[k] = fma(-lij, Ssh[k * LDS_ + j], row[k]);
+    }
+    // the next pivot S[j+1][j+1] is written by thread j+1 only, and read after the barrier at the loop top
+    __syncthreads();
+  }
+  for (int e = i; e < IB * IB; e += IB) {
+    const int r = e / IB, k = e % IB;
+    if (r < w && k < w) A[(int64_t)r * lda + k] = (k <= r) ? Ssh[r * LDS_ + k] : 0.0;
+  }
+}
+
+// recursive Cholesky with 128-wide leaves; panel solves run as GEMMs on the inverted leaf factors
+int potrf128_rec(mb_ctx* ctx, double* A, int64_t lda, int64_t off, int64_t n, int* info, double* inv) {
+  if (n <= 0) return 0;
+  double* D = A + off * lda + off;
+  const size_t smem = (size_t)IB * (IB + 1) * sizeof(double);
+  if (n <= IB) {
+    MB_LAUNCH(ctx, potrf_leaf128_kernel, 1, IB, smem, D, lda, (int)n, off, info);
+    MB_LAUNCH(ctx, tri_inv_blocks_kernel, 1, IB, smem, D, lda, n, inv + (off / IB) * IB * IB);
+    return 0;
+  }
+  const int64_t n1 = ((n / 2 + IB - 1) / IB) * IB, n2 = n - n1;
+  MB_TRY(potrf128_rec(ctx, A, lda, off, n1, info, inv));
+  double* A21 = A + (off + n1) * lda + off;
+  MB_TRY(trsm_inv_rec(ctx, D, lda, inv + (off / IB) * IB * IB, 0, n1, A21, lda, n2));
+  double* A22 = A + (off + n1) * lda + off + n1;
+  MB_TRY(mb_gemm_raw(ctx, false, false, n2, n2, n1, -1.0, A21, lda, A21, lda, 1.0, A22, lda, true));
+  return potrf128_rec(ctx, A, lda, off + n1, n2, info, inv);
+}
+
+int mb_trsm_ws(mb_ctx* ctx, int64_t m) {
+  const size_t need = (size_t)ceil_div64(m, IB) * IB * IB * sizeof(double);
   if (need > ctx->trsm_ws_bytes) {
     MB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->trsm_ws) MB_CUDA(cudaFree(ctx->trsm_ws));
@@ -298,17 +350,37 @@ int mb_trsm_right_lt_raw(mb_ctx* ctx, const double* Lp, int64_t ldl, int64_t m, 
     ctx->trsm_ws_bytes = need;
   }
   static bool configured = false;
-  const size_t smem = (size_t)IB * (IB + 1) * sizeof(double);
   if (!configured) {
-    MB_CUDA(cudaFuncSetAttribute(tri_inv_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int smem = (int)((size_t)IB * (IB + 1) * sizeof(double));
+    MB_CUDA(cudaFuncSetAttribute(tri_inv_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MB_CUDA(cudaFuncSetAttribute(potrf_leaf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
+  return 0;
+}
+
+}  // namespace
+
+int mb_trsm_right_lt_raw(mb_ctx* ctx, const double* Lp, int64_t ldl, int64_t m, double* X, int64_t ldx,
+                         int64_t nrows) {
+  if (nrows <= 0 || m <= 0) return 0;
+  if (ctx->opt_trsm == 1 || nrows < 4 * IB) return trsm_rec(ctx, Lp, ldl, 0, m, X, ldx, nrows);
+  // tall right-hand sides: every flop in the DMMA GEMM (diagonal blocks applied as explicit 128 x 128 inverses)
+  const int64_t nb = ceil_div64(m, IB);
+  const size_t smem = (size_t)IB * (IB + 1) * sizeof(double);
+  MB_TRY(mb_trsm_ws(ctx, m));
   MB_LAUNCH(ctx, tri_inv_blocks_kernel, (int)nb, IB, smem, Lp, ldl, m, ctx->trsm_ws);
   return trsm_inv_rec(ctx, Lp, ldl, ctx->trsm_ws, 0, m, X, ldx, nrows);
 }
 
 int mb_potrf_raw(mb_ctx* ctx, double* A, int64_t n, int64_t lda, int* info_dev) {
-  MB_TRY(potrf_rec(ctx, A, lda, 0, n, info_dev));
+  if (ctx->opt_trsm == 1 || n <= 32) {
+    MB_TRY(potrf_rec(ctx, A, lda, 0, n, info_dev));
+  } else {
+    // NB: the TRSM workspace is overwritten leaf by leaf; a later mb_trsm_right_lt recomputes it
+    MB_TRY(mb_trsm_ws(ctx, n));
+    MB_TRY(potrf128_rec(ctx, A, lda, 0, n, info_dev, ctx->trsm_ws));
+  }
   if (n > 0) {
     dim3 grid((unsigned)ceil_div64(n, 256), (unsigned)n);
     MB_CHECK(n < 65536 * 1, "mb_potrf: n=%lld too large for the zero-upper grid", (long long)n);

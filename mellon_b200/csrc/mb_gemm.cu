@@ -6,15 +6,16 @@
 //   A(i,k) = A[i*lda + k] (AK=false)  or  A[k*lda + i] (AK=true,  "k-major")
 //   B(j,k) = B[j*ldb + k] (BK=false)  or  B[k*ldb + j] (BK=true)
 //
-// CTA tile 128x128x16; 16 warps (4 x 4), warp tile 32x32 = 4x4 DMMA tiles (default) or 8 warps (2 x 4),
+// CTA tile 128x128x32 (one barrier per 32 k: tools/microbench_fp64 shows 34.5 TF with a barrier per 16 k,
+// 35.6 TF per 32 k, 37.0 TF without); 16 warps (4 x 4), warp tile 32x32 = 4x4 DMMA tiles (default) or 8 warps (2 x 4),
 // warp tile 64x32 (opt_gemm = 2).  Symmetric (lower-only) products split the long k axis so that
 // tiles x splits fills whole waves of 148 CTAs; the partial tiles are summed in a fixed order.
 #include "mb_common.cuh"
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BKT = 16, STAGES = 3;
-constexpr int LD_ROWMAJ = BKT + 4;   // [tile_rows][BKT+4]   (stride 20: 4*m + k distinct mod 16)
+constexpr int BM = 128, BN = 128, BKT = 32, STAGES = 3;
+constexpr int LD_ROWMAJ = BKT + 4;   // [tile_rows][BKT+4]   (stride 36 = 4 mod 16: 4*m + k distinct mod 16)
 constexpr int LD_KMAJ = BM + 4;      // [BKT][tile_rows+4]   (stride 132: 4*k + m distinct mod 16)
 constexpr int TILE_DOUBLES = BM * LD_ROWMAJ;  // 2560 >= BKT * LD_KMAJ (2112)
 constexpr size_t SMEM_BYTES = (size_t)STAGES * 2 * TILE_DOUBLES * sizeof(double);
@@ -101,7 +102,51 @@ __device__ __forceinline__ void load_tile(double* dst, const double* __restrict_
   }
 }
 
-template <bool AK, bool BK, int WARPS_M>
+
+// Per-thread operand loader with everything but the k advance hoisted out of the k loop: each of the 512
+// threads owns 4 16-byte chunks of a 128 x 32 operand tile; pointers, shared-memory offsets and edge
+// predicates are computed once per output tile, a k-tile costs 4 cp.async + one pointer bump.  (The generic
+// `load_tile` recomputed ~300 integer instructions per operand per k-tile between the barrier and the first
+// DMMA — the main reason the tensor pipe sat at 81 % busy.)  Needs 16-byte-aligned operands and a full k-tile.
+template <bool KMAJ>
+struct FastLoader {
+  const double* g0;      // chunk 0 of the next k-tile
+  int64_t chunk_stride;  // doubles between this thread's consecutive chunks
+  int64_t ktile_stride;  // doubles per k-tile advance
+  uint32_t s0;           // shared-memory offset (doubles) of chunk 0 inside the operand tile
+  uint32_t nb;           // bytes to copy per chunk (4 x 8 bit); 0 => zero fill (edge rows / columns)
+  static constexpr uint32_t SCS = KMAJ ? 8 * LD_KMAJ : 32 * LD_ROWMAJ;
+
+  __device__ __forceinline__ void init(const double* src, int64_t ld, int64_t r0, int64_t nr, int64_t kbeg, int tid) {
+    nb = 0;
+    if (!KMAJ) {
+      const int r = tid >> 4, c = (tid & 15) * 2;
+      g0 = src + (r0 + r) * ld + kbeg + c;
+      chunk_stride = 32 * ld;
+      ktile_stride = BKT;
+      s0 = r * LD_ROWMAJ + c;
+#pragma unroll
+      for (int it = 0; it < 4; it++) nb |= ((r0 + r + 32 * it < nr) ? 16u : 0u) << (8 * it);
+    } else {
+      const int kk = tid >> 6, c = (tid & 63) * 2;
+      g0 = src + (kbeg + kk) * ld + r0 + c;
+      chunk_stride = 8 * ld;
+      ktile_stride = (int64_t)BKT * ld;
+      s0 = kk * LD_KMAJ + c;
+      const int64_t rem = nr - (r0 + c);
+      const uint32_t b = rem >= 2 ? 16u : (rem == 1 ? 8u : 0u);
+      nb = b | (b << 8) | (b << 16) | (b << 24);
+    }
+  }
+  __device__ __forceinline__ void load(double* dst) {
+#pragma unroll
+    for (int it = 0; it < 4; it++) cp_async16(dst + s0 + it * SCS, g0 + it * chunk_stride, (int)((nb >> (8 * it)) & 255u));
+    g0 += ktile_stride;
+  }
+  __device__ __forceinline__ void skip() { g0 += ktile_stride; }
+};
+
+template <bool AK, bool BK, int WARPS_M, bool FAST>
 __global__ void __launch_bounds__(WARPS_M * 128, 1)
 gemm_dmma_kernel(int64_t m, int64_t n, int64_t k_total, double alpha, const double* __restrict__ A, int64_t lda,
                  const double* __restrict__ B, int64_t ldb, double beta, double* __restrict__ C,
@@ -140,14 +185,28 @@ gemm_dmma_kernel(int64_t m, int64_t n, int64_t k_total, double alpha, const doub
 #pragma unroll
       for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    // operand loaders: FAST (template) = hoisted loaders for full k-tiles of 16-byte-aligned operands
+    FastLoader<AK> la;
+    FastLoader<BK> lb;
+    if (FAST) {
+      la.init(A, lda, m0, m, kbeg, tid);
+      lb.init(B, ldb, n0, n, kbeg, tid);
+    }
+
     // prologue
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
       if (s < nkt) {
         double* sa = smem + (size_t)s * 2 * TILE_DOUBLES;
         double* sb = sa + TILE_DOUBLES;
-        load_tile<AK, NTHREADS>(sa, A, lda, m0, m, kbeg + (int64_t)s * BKT, k, a_vec, tid);
-        load_tile<BK, NTHREADS>(sb, B, ldb, n0, n, kbeg + (int64_t)s * BKT, k, b_vec, tid);
+        const int64_t k0 = kbeg + (int64_t)s * BKT;
+        if (FAST && k0 + BKT <= k) {
+          la.load(sa);
+          lb.load(sb);
+        } else {
+          load_tile<AK, NTHREADS>(sa, A, lda, m0, m, k0, k, a_vec, tid);
+          load_tile<BK, NTHREADS>(sb, B, ldb, n0, n, k0, k, b_vec, tid);
+        }
       }
       cp_async_commit();
     }
@@ -156,13 +215,18 @@ gemm_dmma_kernel(int64_t m, int64_t n, int64_t k_total, double alpha, const doub
       cp_async_wait<STAGES - 2>();
       __syncthreads();
       {
-        int64_t nt = kt + STAGES - 1;
+        const int64_t nt = kt + STAGES - 1;
         if (nt < nkt) {
-          int s = (int)(nt % STAGES);
-          double* sa = smem + (size_t)s * 2 * TILE_DOUBLES;
+          double* sa = smem + (size_t)(nt % STAGES) * 2 * TILE_DOUBLES;
           double* sb = sa + TILE_DOUBLES;
-          load_tile<AK, NTHREADS>(sa, A, lda, m0, m, kbeg + nt * BKT, k, a_vec, tid);
-          load_tile<BK, NTHREADS>(sb, B, ldb, n0, n, kbeg + nt * BKT, k, b_vec, tid);
+          const int64_t k0 = kbeg + nt * BKT;
+          if (FAST && k0 + BKT <= k) {
+            la.load(sa);
+            lb.load(sb);
+          } else {
+            load_tile<AK, NTHREADS>(sa, A, lda, m0, m, k0, k, a_vec, tid);
+            load_tile<BK, NTHREADS>(sb, B, ldb, n0, n, k0, k, b_vec, tid);
+          }
         }
         cp_async_commit();
       }
@@ -311,8 +375,9 @@ int launch_gemm(mb_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, cons
   }
   static bool configured = false;
   if (!configured) {
-    MB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<AK, BK, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    MB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<AK, BK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    MB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<AK, BK, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    MB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<AK, BK, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    MB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<AK, BK, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     configured = true;
   }
   int64_t tm = ceil_div64(m, BM), tn = ceil_div64(n, BN);
@@ -351,10 +416,13 @@ int launch_gemm(mb_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, cons
   int b_vec = ((ldb & 1) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
   if (ctx->prof_on) ctx->prof_work[MB_PROF_GEMM] += (lower_only ? 1.0 : 2.0) * (double)m * (double)n * (double)k;
   if (ctx->opt_gemm == 2) {
-    MB_LAUNCH_P(ctx, MB_PROF_GEMM, (gemm_dmma_kernel<AK, BK, 2>), grid, 256, SMEM_BYTES, m, n, k, alpha, A, lda, B, ldb,
+    MB_LAUNCH_P(ctx, MB_PROF_GEMM, (gemm_dmma_kernel<AK, BK, 2, false>), grid, 256, SMEM_BYTES, m, n, k, alpha, A, lda, B, ldb,
+                beta, C, ldc, lower_only ? 1 : 0, tn, nt, a_vec, b_vec, ksplit, kchunk, ws, ws_stride);
+  } else if (a_vec && b_vec && ctx->opt_gemm != 4) {
+    MB_LAUNCH_P(ctx, MB_PROF_GEMM, (gemm_dmma_kernel<AK, BK, 4, true>), grid, 512, SMEM_BYTES, m, n, k, alpha, A, lda, B, ldb,
                 beta, C, ldc, lower_only ? 1 : 0, tn, nt, a_vec, b_vec, ksplit, kchunk, ws, ws_stride);
   } else {
-    MB_LAUNCH_P(ctx, MB_PROF_GEMM, (gemm_dmma_kernel<AK, BK, 4>), grid, 512, SMEM_BYTES, m, n, k, alpha, A, lda, B, ldb,
+    MB_LAUNCH_P(ctx, MB_PROF_GEMM, (gemm_dmma_kernel<AK, BK, 4, false>), grid, 512, SMEM_BYTES, m, n, k, alpha, A, lda, B, ldb,
                 beta, C, ldc, lower_only ? 1 : 0, tn, nt, a_vec, b_vec, ksplit, kchunk, ws, ws_stride);
   }
   if (ksplit > 1) {

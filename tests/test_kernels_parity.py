@@ -133,11 +133,16 @@ def _spd(n, seed, cond=1e6):
     return (q * ev) @ q.T
 
 
-@pytest.mark.parametrize("n", [1, 5, 32, 33, 100, 257, 1000])
-def test_potrf(be, n):
+@pytest.mark.parametrize("variant", [0, 1], ids=["leaf128", "leaf32"])
+@pytest.mark.parametrize("n", [1, 5, 32, 33, 100, 128, 129, 257, 1000, 1700])
+def test_potrf(be, variant, n):
     A = _spd(n, n)
     Ad = be.upload(A.copy())
-    assert be.potrf(Ad) == 0
+    be.set_option("trsm", variant)
+    try:
+        assert be.potrf(Ad) == 0
+    finally:
+        be.set_option("trsm", 0)
     Lc = Ad.numpy()
     Lref = np.linalg.cholesky(A)
     assert np.allclose(np.triu(Lc, 1), 0.0)
@@ -150,6 +155,10 @@ def test_potrf_reports_non_positive_definite(be):
     A[40, 40] = -1.0
     info = be.potrf(be.upload(A))
     assert 1 <= info <= 41
+    A = _spd(300, 1)
+    A[200, 200] = -1.0
+    info = be.potrf(be.upload(A))
+    assert 129 <= info <= 201
 
 
 @pytest.mark.parametrize("variant", [0, 1], ids=["inv128-gemm-leaves", "substitution-leaves"])
