@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region (A/B only)")
+    ap.add_argument("--predict-queries", type=int, default=1_000_000,
+                    help="out-of-sample queries for the extra predict() measurement (BASELINE config 5 shape); 0 = skip")
     return ap.parse_args()
 
 
@@ -248,10 +250,13 @@ def run_b200(args):
         sampler.start()
     be.timer_start(0)
     nfev = []
+    last_est = None
     for _ in range(args.steps):
+        last_est = None  # frees the previous step's 40 GB factor before the next one is built
         est, dens = step(xd)
         nfev.append(int(est.opt_state.num_fun_eval))
         nit = int(est.opt_state.iter_num)
+        last_est = est
         del est
     ms = be.timer_stop(0)
     be.sync()
@@ -264,6 +269,30 @@ def run_b200(args):
     ms_per_step = ms / args.steps
     value = args.cells / (ms_per_step * 1e-3)
     checksum = float(np.sum(dens))
+
+    # --- predict(): conditional-mean kernel K7 on out-of-sample queries (host in, host out) ---------
+    predict = None
+    if args.predict_queries > 0:
+        q_total = args.predict_queries
+        xq = np.random.default_rng(2).random((q_total, args.dims))
+        predictor = last_est.predict          # builds the predictor: weights = Lp^-T z
+        predictor(xq[:1024])                  # warm-up
+        be.prof_enable(True)
+        be.prof_reset()
+        dist.barrier()
+        be.sync()
+        t0 = time.perf_counter()
+        pq = predictor(xq)
+        be.sync()
+        dt_q = dist.host_max(time.perf_counter() - t0)
+        n_mv, ms_mv, _ = be.prof_read()["matvec"]
+        be.prof_enable(False)
+        predict = {"queries": q_total, "value": q_total / dt_q, "unit": "queries/s (host in, host out, all GPUs)",
+                   "k7_kernel_ms": ms_mv, "k7_launches": n_mv,
+                   "k7_elements_per_s": (q_total / max(world, 1)) * args.landmarks / (ms_mv * 1e-3) if ms_mv else None,
+                   "checksum": float(np.sum(pq))}
+        del predictor, xq
+    last_est = None
 
     # --- end-to-end arm: host buffers in, host result out -----------------------------------------
     e2e = None
@@ -331,12 +360,19 @@ def run_b200(args):
         dens_s = mb.DensityEstimator(cov_func_curry=cov_curry, landmarks=lms, nn_distances=nns,
                                      check_rank=False).fit_predict(xs)
         ref_s = np.asarray(fit.log_density_x)
+        diff = dens_s - ref_s
         parity = {
             "sample": f"first {ns} cells, all {args.landmarks} landmarks: CUDA fit_predict vs the CPU oracle's",
-            "max_rel_err_log_density": float(np.max(np.abs(dens_s - ref_s) / np.abs(ref_s))),
-            "max_abs_err_over_max_abs": float(np.max(np.abs(dens_s - ref_s)) / np.max(np.abs(ref_s))),
+            # the reference's own acceptance metric (tests/test_density_estimator.py:30-44): std(a - b) / std(b)
+            "rel_std_err_log_density": float(np.std(diff) / np.std(ref_s)),
+            "max_abs_err_over_max_abs": float(np.max(np.abs(diff)) / np.max(np.abs(ref_s))),
+            # element-wise relative error: log densities cross zero on this workload, so this one is dominated by
+            # the cells whose log density is ~0 (reported for completeness, not judged)
+            "max_elementwise_rel_err": float(np.max(np.abs(diff) / np.abs(ref_s))),
+            "min_abs_log_density": float(np.min(np.abs(ref_s))), "max_abs_log_density": float(np.max(np.abs(ref_s))),
             "tolerance": 1e-5,
         }
+        parity["ok"] = bool(parity["rel_std_err_log_density"] < 1e-5 and parity["max_abs_err_over_max_abs"] < 1e-5)
         cpu_baseline = {
             "value": ns / dt, "unit": UNIT, "cores": threads_used(), "kind": "port",
             "sample": f"first {ns} cells of the workload (all {args.landmarks} landmarks, their nn_distances taken "
@@ -350,7 +386,7 @@ def run_b200(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
-        "cpu_baseline": cpu_baseline, "parity": parity, "lbfgsb": {"nfev_per_step": nfev, "nit_last": nit},
+        "predict": predict, "cpu_baseline": cpu_baseline, "parity": parity, "lbfgsb": {"nfev_per_step": nfev, "nit_last": nit},
         "log_density_checksum": checksum,
     }
     print(json.dumps(line))

@@ -40,6 +40,7 @@ extern "C" int mb_ctx_create(int device, mb_ctx** out) {
   mb_ctx* c = new mb_ctx();
   c->device = device;
   c->n_sm = prop.multiProcessorCount;
+  c->cache_cap = (size_t)(0.45 * (double)prop.totalGlobalMem);  // at most 45 % of HBM parked in the block cache
   MB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   MB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 16; i++)
@@ -52,11 +53,28 @@ extern "C" int mb_ctx_create(int device, mb_ctx** out) {
   return 0;
 }
 
+void mb_cache_flush(mb_ctx* c) {
+  for (auto& kv : c->block_cache) cudaFree(kv.second);
+  c->block_cache.clear();
+  c->cached_bytes = 0;
+}
+
+cudaError_t mb_dev_malloc(mb_ctx* c, void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess && !c->block_cache.empty()) {
+    cudaGetLastError();
+    mb_cache_flush(c);
+    e = cudaMalloc(p, bytes);
+  }
+  return e;
+}
+
 extern "C" int mb_ctx_destroy(mb_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   mb_comm_destroy(c);
+  mb_cache_flush(c);
   if (c->scratch) cudaFree(c->scratch);
   if (c->flush_buf) cudaFree(c->flush_buf);
   if (c->gemm_ws) cudaFree(c->gemm_ws);
@@ -185,7 +203,7 @@ int mb_scratch(mb_ctx* c, size_t bytes, double** out) {
     c->scratch = nullptr;
     c->scratch_bytes = 0;
     size_t want = bytes + bytes / 4;
-    MB_CUDA(cudaMalloc(&c->scratch, want));
+    MB_CUDA(mb_dev_malloc(c, (void**)&c->scratch, want));
     c->scratch_bytes = want;
   }
   *out = c->scratch;
@@ -327,7 +345,23 @@ extern "C" int mb_mat_alloc(mb_ctx* c, int64_t rows, int64_t cols, mb_mat** out)
   m->p = nullptr;
   size_t bytes = (size_t)rows * (size_t)cols * sizeof(double);
   if (bytes > 0) {
+    // a cached block of the same size class (at most 1/8 larger)?
+    auto it = c->block_cache.lower_bound(bytes);
+    if (it != c->block_cache.end() && it->first <= bytes + bytes / 8) {
+      m->p = it->second;
+      m->alloc_bytes = it->first;
+      c->cached_bytes -= it->first;
+      c->block_cache.erase(it);
+      *out = m;
+      return 0;
+    }
     cudaError_t e = cudaMalloc(&m->p, bytes);
+    if (e != cudaSuccess && !c->block_cache.empty()) {
+      cudaGetLastError();
+      mb_cache_flush(c);
+      e = cudaMalloc(&m->p, bytes);
+    }
+    m->alloc_bytes = bytes;
     if (e != cudaSuccess) {
       delete m;
       mb_set_error("mb_mat_alloc: cudaMalloc of %zu bytes (%lld x %lld f64) failed: %s", bytes,
@@ -346,7 +380,14 @@ extern "C" int mb_mat_free(mb_ctx* c, mb_mat* m) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
   }
-  if (m->owns && m->p) cudaFree(m->p);
+  if (m->owns && m->p) {
+    if (c && m->alloc_bytes >= ((size_t)1 << 20) && c->cached_bytes + m->alloc_bytes <= c->cache_cap) {
+      c->block_cache.emplace(m->alloc_bytes, m->p);
+      c->cached_bytes += m->alloc_bytes;
+    } else {
+      cudaFree(m->p);
+    }
+  }
   delete m;
   return 0;
 }

@@ -92,31 +92,49 @@ int trsm_rec(mb_ctx* ctx, const double* Lp, int64_t ldl, int64_t c0, int64_t w, 
 
 
 // ---- inverse of the 128-wide diagonal blocks of a lower-triangular matrix -----------------------
-// One CTA per block, thread c solves T x = e_c by forward substitution (column c of T^-1); T is
-// staged in shared memory.  Output: dense 128 x 128 blocks (zero above the diagonal and beyond w).
-constexpr int IB = 128;
-__global__ void __launch_bounds__(IB)
+// One CTA of 32 warps per block, T staged in shared memory ([IB][IB + 1]).  Warp q owns columns
+// q, q + 32, q + 64, q + 96 of T^-1: forward substitution down the column, the dot product of each row
+// split over the lanes and reduced by shuffles (fixed order), x kept in a per-warp shared-memory strip.
+// Output: dense 128 x 128 blocks (zero above the diagonal and beyond w).
+constexpr int IB = 128, IBT = 1024, ILD = IB + 1;
+constexpr size_t IB_SMEM = ((size_t)IB * ILD + (size_t)(IBT / 32) * IB + IB) * sizeof(double);
+
+// Tsh: factor block (diagonal included), xw: (IBT/32) x IB strip, rdiag: IB reciprocals of the diagonal
+__device__ __forceinline__ void tri_inv_block(const double* Tsh, double* xw_all, double* rdiag, int w,
+                                              double* __restrict__ out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < IB) rdiag[tid] = (tid < w) ? 1.0 / Tsh[tid * ILD + tid] : 0.0;
+  __syncthreads();
+  double* xw = xw_all + warp * IB;
+  for (int c = warp; c < IB; c += IBT / 32) {
+    if (c < w) {
+      for (int r = c; r < w; r++) {
+        double s = 0.0;
+        for (int k = c + lane; k < r; k += 32) s = fma(Tsh[r * ILD + k], xw[k], s);
+        s = warp_sum(s);
+        const double v = (((r == c) ? 1.0 : 0.0) - s) * rdiag[r];
+        if (lane == 0) xw[r] = v;
+        __syncwarp();
+      }
+    }
+    for (int r = lane; r < IB; r += 32) out[(int64_t)r * IB + c] = (c < w && r >= c && r < w) ? xw[r] : 0.0;
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(IBT)
 tri_inv_blocks_kernel(const double* __restrict__ L, int64_t ldl, int64_t m, double* __restrict__ inv) {
-  extern __shared__ double Tsh[];  // IB x (IB + 1)
+  extern __shared__ double Tsh[];  // IB x ILD, then the per-warp strips, then the reciprocal diagonal
+  double* xw = Tsh + IB * ILD;
+  double* rdiag = xw + (IBT / 32) * IB;
   const int64_t j0 = (int64_t)blockIdx.x * IB;
   const int w = (int)min((int64_t)IB, m - j0);
-  const int c = threadIdx.x;
-  for (int e = c; e < IB * IB; e += IB) {
+  for (int e = threadIdx.x; e < IB * IB; e += IBT) {
     const int r = e / IB, k = e % IB;
-    Tsh[r * (IB + 1) + k] = (r < w && k < w && k <= r) ? L[(j0 + r) * ldl + j0 + k] : 0.0;
+    Tsh[r * ILD + k] = (r < w && k < w && k <= r) ? L[(j0 + r) * ldl + j0 + k] : 0.0;
   }
   __syncthreads();
-  double* out = inv + (int64_t)blockIdx.x * IB * IB;
-  // column c of the inverse lives in x[] = out[:, c]; rows above c are zero
-  for (int r = 0; r < IB; r++) {
-    double v = 0.0;
-    if (c < w && r < w && r >= c) {
-      double s = (r == c) ? 1.0 : 0.0;
-      for (int k = c; k < r; k++) s = fma(-Tsh[r * (IB + 1) + k], out[(int64_t)k * IB + c], s);
-      v = s / Tsh[r * (IB + 1) + r];
-    }
-    out[(int64_t)r * IB + c] = v;  // each thread re-reads only its own column: no barrier needed
-  }
+  tri_inv_block(Tsh, xw, rdiag, w, inv + (int64_t)blockIdx.x * IB * IB);
 }
 
 // X[:, c0:c0+w] <- X[:, c0:c0+w] Lp[c0:c0+w, c0:c0+w]^-T with GEMM leaves on the inverted diagonal blocks
@@ -281,53 +299,55 @@ trsv_kernel(const double* __restrict__ L, int64_t ldl, int m, double* __restrict
 }
 
 
-// ---- leaf: Cholesky of one (w <= 128) diagonal block in shared memory, one thread per row ----
-__global__ void __launch_bounds__(IB)
-potrf_leaf128_kernel(double* __restrict__ A, int64_t lda, int w, int64_t global_off, int* info) {
-  extern __shared__ double Ssh[];  // IB x (IB + 1)
-  const int i = threadIdx.x;
-  constexpr int LDS_ = IB + 1;
-  for (int e = i; e < IB * IB; e += IB) {
+// ---- leaf: Cholesky of one (w <= 128) diagonal block in shared memory + the inverse of its factor -----
+// 1024 threads: thread (i = tid & 127, q = tid >> 7) updates columns k = j + 1 + q (mod 8) of row i in the
+// rank-1 update of column j; two barriers per column.  The factor goes back to A, its inverse to `inv_out`.
+__global__ void __launch_bounds__(IBT)
+potrf_inv_leaf128_kernel(double* __restrict__ A, int64_t lda, int w, int64_t global_off, int* info,
+                         double* __restrict__ inv_out) {
+  extern __shared__ double Ssh[];
+  double* xw = Ssh + IB * ILD;
+  double* rdiag = xw + (IBT / 32) * IB;
+  const int tid = threadIdx.x, i = tid & (IB - 1), q = tid >> 7;
+  for (int e = tid; e < IB * IB; e += IBT) {
     const int r = e / IB, k = e % IB;
-    Ssh[r * LDS_ + k] = (r < w && k <= r) ? A[(int64_t)r * lda + k] : 0.0;
+    Ssh[r * ILD + k] = (r < w && k <= r) ? A[(int64_t)r * lda + k] : 0.0;
   }
   __syncthreads();
   for (int j = 0; j < w; j++) {
-    double d = Ssh[j * LDS_ + j];
+    // S[j][j] is final after the previous column's update and is not written during this column
+    double d = Ssh[j * ILD + j];
     if (!(d > 0.0)) {
-      if (i == 0) atomicCAS(info, 0, (int)(global_off + j + 1));
+      if (tid == 0) atomicCAS(info, 0, (int)(global_off + j + 1));
       d = nan("");
     }
     d = sqrt(d);
-    __syncthreads();
-    double lij = 0.0;
-    if (i == j) Ssh[j * LDS_ + j] = d;
-    if (i > j && i < w) {
-      lij = Ssh[i * LDS_ + j] / d;
-      Ssh[i * LDS_ + j] = lij;
-    }
+    if (q == 0 && i > j && i < w) Ssh[i * ILD + j] = Ssh[i * ILD + j] / d;
+    if (tid == 0) rdiag[j] = d;  // the pivot itself is parked here until the loop is over
     __syncthreads();
     if (i > j && i < w) {
-      double* row = Ssh + i * LDS_;
-      for (int k = j + 1; k <= i; k++) row[k] = fma(-lij, Ssh[k * LDS_ + j], row[k]);
+      const double lij = Ssh[i * ILD + j];
+      double* row = Ssh + i * ILD;
+      for (int k = j + 1 + q; k <= i; k += IBT / IB) row[k] = fma(-lij, Ssh[k * ILD + j], row[k]);
     }
-    // the next pivot S[j+1][j+1] is written by thread j+1 only, and read after the barrier at the loop top
     __syncthreads();
   }
-  for (int e = i; e < IB * IB; e += IB) {
+  if (tid < w) Ssh[tid * ILD + tid] = rdiag[tid];
+  __syncthreads();
+  for (int e = tid; e < IB * IB; e += IBT) {
     const int r = e / IB, k = e % IB;
-    if (r < w && k < w) A[(int64_t)r * lda + k] = (k <= r) ? Ssh[r * LDS_ + k] : 0.0;
+    if (r < w && k < w) A[(int64_t)r * lda + k] = (k <= r) ? Ssh[r * ILD + k] : 0.0;
   }
+  __syncthreads();
+  tri_inv_block(Ssh, xw, rdiag, w, inv_out);
 }
 
 // recursive Cholesky with 128-wide leaves; panel solves run as GEMMs on the inverted leaf factors
 int potrf128_rec(mb_ctx* ctx, double* A, int64_t lda, int64_t off, int64_t n, int* info, double* inv) {
   if (n <= 0) return 0;
   double* D = A + off * lda + off;
-  const size_t smem = (size_t)IB * (IB + 1) * sizeof(double);
   if (n <= IB) {
-    MB_LAUNCH(ctx, potrf_leaf128_kernel, 1, IB, smem, D, lda, (int)n, off, info);
-    MB_LAUNCH(ctx, tri_inv_blocks_kernel, 1, IB, smem, D, lda, n, inv + (off / IB) * IB * IB);
+    MB_LAUNCH(ctx, potrf_inv_leaf128_kernel, 1, IBT, IB_SMEM, D, lda, (int)n, off, info, inv + (off / IB) * IB * IB);
     return 0;
   }
   const int64_t n1 = ((n / 2 + IB - 1) / IB) * IB, n2 = n - n1;
@@ -346,17 +366,74 @@ int mb_trsm_ws(mb_ctx* ctx, int64_t m) {
     if (ctx->trsm_ws) MB_CUDA(cudaFree(ctx->trsm_ws));
     ctx->trsm_ws = nullptr;
     ctx->trsm_ws_bytes = 0;
-    MB_CUDA(cudaMalloc(&ctx->trsm_ws, need));
+    MB_CUDA(mb_dev_malloc(ctx, (void**)&ctx->trsm_ws, need));
     ctx->trsm_ws_bytes = need;
   }
   static bool configured = false;
   if (!configured) {
-    const int smem = (int)((size_t)IB * (IB + 1) * sizeof(double));
-    MB_CUDA(cudaFuncSetAttribute(tri_inv_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    MB_CUDA(cudaFuncSetAttribute(potrf_leaf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MB_CUDA(cudaFuncSetAttribute(tri_inv_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IB_SMEM));
+    MB_CUDA(cudaFuncSetAttribute(potrf_inv_leaf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IB_SMEM));
     configured = true;
   }
   return 0;
+}
+
+
+// ---- blocked vector triangular solve on the inverted 128-blocks ------------------------------------
+// forward (L x = b):   for j = 0 .. nb-1:  x_j = Dinv_j b_j ;  b_(>j) -= L_(>j, j) x_j
+// backward (L^T x = b): for j = nb-1 .. 0:  x_j = Dinv_j^T b_j ; b_(<j) -= L_(j, <j)^T x_j
+// Two small launches per block instead of one CTA walking the whole 200 MB factor.
+__global__ void __launch_bounds__(IBT)
+trsv_diag_kernel(const double* __restrict__ inv, int w, int trans, double* __restrict__ b) {
+  __shared__ double bs[IB], xs[IB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < IB) bs[tid] = (tid < w) ? b[tid] : 0.0;
+  __syncthreads();
+  if (!trans) {
+    // x[r] = sum_c inv[r][c] b[c]: warp per 4 rows, lanes across the row
+    for (int r = warp; r < w; r += IBT / 32) {
+      double s = 0.0;
+      for (int c = lane; c <= r; c += 32) s = fma(inv[(int64_t)r * IB + c], bs[c], s);
+      s = warp_sum(s);
+      if (lane == 0) xs[r] = s;
+    }
+  } else if (tid < IB) {
+    // x[c] = sum_r inv[r][c] b[r]: thread per column, coalesced across the row
+    double s = 0.0;
+    for (int r = tid; r < w; r++) s = fma(inv[(int64_t)r * IB + tid], bs[r], s);
+    xs[tid] = s;
+  }
+  __syncthreads();
+  if (tid < w) b[tid] = xs[tid];
+}
+// forward update: rows below block j; one warp per row
+__global__ void __launch_bounds__(256)
+trsv_update_fwd_kernel(const double* __restrict__ L, int64_t ldl, int64_t row0, int64_t m, int64_t col0, int w,
+                       double* __restrict__ b) {
+  __shared__ double xs[IB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < IB) xs[tid] = (tid < w) ? b[col0 + tid] : 0.0;
+  __syncthreads();
+  const int64_t r = row0 + (int64_t)blockIdx.x * 8 + warp;
+  if (r >= m) return;
+  double s = 0.0;
+  for (int c = lane; c < w; c += 32) s = fma(L[r * ldl + col0 + c], xs[c], s);
+  s = warp_sum(s);
+  if (lane == 0) b[r] -= s;
+}
+// backward update: columns left of block j; one thread per column
+__global__ void __launch_bounds__(256)
+trsv_update_bwd_kernel(const double* __restrict__ L, int64_t ldl, int64_t row0, int w, int64_t ncols,
+                       double* __restrict__ b) {
+  __shared__ double xs[IB];
+  const int tid = threadIdx.x;
+  if (tid < IB) xs[tid] = (tid < w) ? b[row0 + tid] : 0.0;
+  __syncthreads();
+  const int64_t c = (int64_t)blockIdx.x * 256 + tid;
+  if (c >= ncols) return;
+  double s = 0.0;
+  for (int r = 0; r < w; r++) s = fma(L[(row0 + r) * ldl + c], xs[r], s);
+  b[c] -= s;
 }
 
 }  // namespace
@@ -367,9 +444,8 @@ int mb_trsm_right_lt_raw(mb_ctx* ctx, const double* Lp, int64_t ldl, int64_t m, 
   if (ctx->opt_trsm == 1 || nrows < 4 * IB) return trsm_rec(ctx, Lp, ldl, 0, m, X, ldx, nrows);
   // tall right-hand sides: every flop in the DMMA GEMM (diagonal blocks applied as explicit 128 x 128 inverses)
   const int64_t nb = ceil_div64(m, IB);
-  const size_t smem = (size_t)IB * (IB + 1) * sizeof(double);
   MB_TRY(mb_trsm_ws(ctx, m));
-  MB_LAUNCH(ctx, tri_inv_blocks_kernel, (int)nb, IB, smem, Lp, ldl, m, ctx->trsm_ws);
+  MB_LAUNCH(ctx, tri_inv_blocks_kernel, (int)nb, IBT, IB_SMEM, Lp, ldl, m, ctx->trsm_ws);
   return trsm_inv_rec(ctx, Lp, ldl, ctx->trsm_ws, 0, m, X, ldx, nrows);
 }
 
@@ -422,6 +498,26 @@ extern "C" int mb_tri_solve(mb_ctx* ctx, const mb_mat* Lp, int trans, mb_mat* B)
   MB_CUDA(cudaSetDevice(ctx->device));
   const int64_t m = Lp->rows, nrhs = B->cols;
   if (m == 0 || nrhs == 0) return 0;
+  if (nrhs == 1 && m > 2 * IB && ctx->opt_trsm != 1) {
+    const int64_t nb = ceil_div64(m, IB);
+    MB_TRY(mb_trsm_ws(ctx, m));
+    MB_LAUNCH(ctx, tri_inv_blocks_kernel, (int)nb, IBT, IB_SMEM, Lp->p, Lp->cols, m, ctx->trsm_ws);
+    const int64_t ldl = Lp->cols;
+    for (int64_t jj = 0; jj < nb; jj++) {
+      const int64_t j = trans ? nb - 1 - jj : jj;
+      const int64_t j0 = j * IB;
+      const int w = (int)min((int64_t)IB, m - j0);
+      MB_LAUNCH(ctx, trsv_diag_kernel, 1, IBT, 0, ctx->trsm_ws + j * IB * IB, w, trans ? 1 : 0, B->p + j0);
+      if (!trans) {
+        const int64_t row0 = j0 + w;
+        if (row0 < m)
+          MB_LAUNCH(ctx, trsv_update_fwd_kernel, (int)ceil_div64(m - row0, 8), 256, 0, Lp->p, ldl, row0, m, j0, w, B->p);
+      } else if (j0 > 0) {
+        MB_LAUNCH(ctx, trsv_update_bwd_kernel, (int)ceil_div64(j0, 256), 256, 0, Lp->p, ldl, j0, w, j0, B->p);
+      }
+    }
+    return 0;
+  }
   const size_t smem = (size_t)m * sizeof(double);
   if (nrhs <= 64 && smem <= 200 * 1024) {
     static bool configured = false;

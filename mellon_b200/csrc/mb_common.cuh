@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -16,6 +17,7 @@ struct mb_mat {
   int64_t rows, cols;
   mb_ctx* ctx;
   bool owns;
+  size_t alloc_bytes = 0;  // size of the device block behind p (>= rows * cols * 8 when it came from the cache)
 };
 
 // kernel classes for the in-library stopwatch (mb_prof_*): CUDA events around each launch
@@ -42,6 +44,10 @@ struct mb_ctx {
   size_t pinned_bytes = 0;
   double* flush_buf = nullptr;
   size_t flush_bytes = 0;
+  // device block cache: freed matrices are kept (after a stream sync) and handed back to allocations of the
+  // same size class, so a fit does not pay cudaMalloc / cudaFree of its 40 GB factor every time
+  std::multimap<size_t, double*> block_cache;
+  size_t cached_bytes = 0, cache_cap = 0;
   double* trsm_ws = nullptr;           // inverted 128 x 128 diagonal blocks of the TRSM
   size_t trsm_ws_bytes = 0;
   double* gemm_ws = nullptr;           // split-k partial tiles (own buffer: GEMMs run inside scratch users)
@@ -122,6 +128,9 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 
 // scratch management (grows monotonically; contents undefined)
 int mb_scratch(mb_ctx* ctx, size_t bytes, double** out);
+void mb_cache_flush(mb_ctx* ctx);  // release every cached device block
+// cudaMalloc that empties the block cache and retries once before giving up
+cudaError_t mb_dev_malloc(mb_ctx* ctx, void** p, size_t bytes);
 int mb_pinned(mb_ctx* ctx, size_t bytes, double** out);
 
 // internal helpers implemented across translation units

@@ -1099,7 +1099,7 @@ extern "C" int mb_nn_distances(mb_ctx* ctx, const mb_mat* x, const mb_mat* all, 
   mb_kop op = {MB_OP_LEAF, MB_K_DISTANCE, 1.0, 1.0, 0.0, 0, -1};
   mb_kprog prog = {1, 0, &op, nullptr};
   int64_t* idx_dev = nullptr;
-  MB_CUDA(cudaMalloc(&idx_dev, sizeof(int64_t) * n));
+  MB_CUDA(mb_dev_malloc(ctx, (void**)&idx_dev, sizeof(int64_t) * n));
   int rc = 0;
   {
     Plan plan;

@@ -406,7 +406,7 @@ int launch_gemm(mb_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, cons
       if (ctx->gemm_ws) MB_CUDA(cudaFree(ctx->gemm_ws));
       ctx->gemm_ws = nullptr;
       ctx->gemm_ws_bytes = 0;
-      MB_CUDA(cudaMalloc(&ctx->gemm_ws, need));
+      MB_CUDA(mb_dev_malloc(ctx, (void**)&ctx->gemm_ws, need));
       ctx->gemm_ws_bytes = need;
     }
     ws = ctx->gemm_ws;

@@ -177,7 +177,7 @@ def test_trsm_right(be, variant, n, m):
     assert rel_err(out, ref) < 1e-11
 
 
-@pytest.mark.parametrize("m,nrhs", [(1, 1), (40, 1), (100, 3), (257, 1), (300, 70), (97, 129)])
+@pytest.mark.parametrize("m,nrhs", [(1, 1), (40, 1), (100, 3), (257, 1), (300, 70), (97, 129), (384, 1), (700, 1), (1301, 1)])
 @pytest.mark.parametrize("trans", [False, True])
 def test_tri_solve(be, m, nrhs, trans):
     rng = np.random.default_rng(m * 7 + nrhs)
