@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(WARPS_M * 128, 1)
 gemm_dmma_kernel(int64_t m, int64_t n, int64_t k_total, double alpha, const double* __restrict__ A, int64_t lda,
                  const double* __restrict__ B, int64_t ldb, double beta, double* __restrict__ C,
                  int64_t ldc, int lower_only, int64_t tiles_n, int64_t n_tiles, int a_vec, int b_vec,
-                 int ksplit, int64_t kchunk, double* __restrict__ ws, int64_t ws_stride) {
+                 int ksplit, int64_t kchunk, double* __restrict__ ws, int64_t ws_stride, int64_t ldw) {
   constexpr int NTHREADS = WARPS_M * 128;
   constexpr int WTM = BM / WARPS_M;  // warp tile rows: 64 or 32
   constexpr int MI = WTM / 8;
@@ -257,8 +257,9 @@ gemm_dmma_kernel(int64_t m, int64_t n, int64_t k_total, double alpha, const doub
 
     // epilogue (split-k items store their raw partial tile into the workspace slice of their split)
     double* Cout = (ksplit > 1) ? ws + (int64_t)ss * ws_stride : C;
+    const int64_t ldo = (ksplit > 1) ? ldw : ldc;
     const double alpha_e = (ksplit > 1) ? 1.0 : alpha, beta_e = (ksplit > 1) ? 0.0 : beta;
-    const bool c_vec = ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0);
+    const bool c_vec = ((ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0);
 #pragma unroll
     for (int i = 0; i < MI; i++) {
       int64_t row = m0 + wm0 + i * 8 + lr;
@@ -267,7 +268,7 @@ gemm_dmma_kernel(int64_t m, int64_t n, int64_t k_total, double alpha, const doub
       for (int j = 0; j < 4; j++) {
         int64_t col = n0 + wn0 + j * 8 + lk * 2;
         if (col >= n) continue;
-        double* cp = Cout + row * ldc + col;
+        double* cp = Cout + row * ldo + col;
         double v0 = alpha_e * acc[i][j][0], v1 = alpha_e * acc[i][j][1];
         if (col + 1 < n) {
           if (c_vec) {
@@ -350,14 +351,15 @@ gemm_dfma_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __
 }
 
 // C = alpha * sum_s ws[s] + beta * C over the (lower-triangular tiles of the) output, splits in a fixed order
-__global__ void splitk_reduce_kernel(const double* __restrict__ ws, int ksplit, int64_t ws_stride, int64_t m, int64_t n,
-                                     int64_t ldc, double alpha, double beta, double* __restrict__ C, int lower_only) {
+__global__ void splitk_reduce_kernel(const double* __restrict__ ws, int ksplit, int64_t ws_stride, int64_t ldw, int64_t m,
+                                     int64_t n, int64_t ldc, double alpha, double beta, double* __restrict__ C,
+                                     int lower_only) {
   const int64_t row = blockIdx.y;
   const int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (row >= m || col >= n) return;
   if (lower_only && col / BN > row / BM) return;  // tile never computed
   double s = 0.0;
-  for (int q = 0; q < ksplit; q++) s += ws[(int64_t)q * ws_stride + row * ldc + col];
+  for (int q = 0; q < ksplit; q++) s += ws[(int64_t)q * ws_stride + row * ldw + col];
   double v = alpha * s;
   if (beta != 0.0) v += beta * C[row * ldc + col];
   C[row * ldc + col] = v;
@@ -383,23 +385,27 @@ int launch_gemm(mb_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, cons
   int64_t tm = ceil_div64(m, BM), tn = ceil_div64(n, BN);
   int64_t nt = lower_only ? tm * (tm + 1) / 2 : tm * tn;
   if (lower_only) MB_CHECK(m == n, "gemm lower_only needs a square output");
-  // split the contraction axis when the tile count leaves the last wave of CTAs mostly idle
+  // split the contraction axis when the tile count leaves the last wave of CTAs mostly idle: few tiles (the
+  // mid-size products inside the Cholesky) split down to 512-deep chunks, many tiles only to 4096-deep ones
   int ksplit = 1;
-  if (lower_only && ctx->opt_gemm != 3 && nt > ctx->n_sm / 2) {
-    double best = (double)nt / (double)(ceil_div64(nt, ctx->n_sm) * ctx->n_sm);
+  if (ctx->opt_gemm != 3) {
+    const int64_t sm = ctx->n_sm;
+    const int64_t min_chunk = (nt < 4 * sm) ? 512 : 4096;
+    double best = (double)nt / (double)(ceil_div64(nt, sm) * sm);
     for (int sp = 2; sp <= 16 && best < 0.97; sp++) {
-      if (k / sp < 4096) break;
+      if (k / sp < min_chunk) break;
       const int64_t items = nt * sp;
-      const double eff = (double)items / (double)(ceil_div64(items, ctx->n_sm) * ctx->n_sm);
+      const double eff = (double)items / (double)(ceil_div64(items, sm) * sm);
       if (eff > best + 0.01) { best = eff; ksplit = sp; }
     }
   }
-  int64_t kchunk = k, ws_stride = 0;
+  int64_t kchunk = k, ws_stride = 0, ldw = 0;
   double* ws = nullptr;
   if (ksplit > 1) {
     kchunk = ceil_div64(ceil_div64(k, ksplit), BKT) * BKT;
     ksplit = (int)ceil_div64(k, kchunk);
-    ws_stride = m * ldc;
+    ldw = (n + 1) & ~(int64_t)1;  // dense, even (16-byte rows)
+    ws_stride = m * ldw;
     const size_t need = (size_t)ksplit * ws_stride * sizeof(double);
     if (need > ctx->gemm_ws_bytes) {
       MB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -417,17 +423,17 @@ int launch_gemm(mb_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, cons
   if (ctx->prof_on) ctx->prof_work[MB_PROF_GEMM] += (lower_only ? 1.0 : 2.0) * (double)m * (double)n * (double)k;
   if (ctx->opt_gemm == 2) {
     MB_LAUNCH_P(ctx, MB_PROF_GEMM, (gemm_dmma_kernel<AK, BK, 2, false>), grid, 256, SMEM_BYTES, m, n, k, alpha, A, lda, B, ldb,
-                beta, C, ldc, lower_only ? 1 : 0, tn, nt, a_vec, b_vec, ksplit, kchunk, ws, ws_stride);
+                beta, C, ldc, lower_only ? 1 : 0, tn, nt, a_vec, b_vec, ksplit, kchunk, ws, ws_stride, ldw);
   } else if (a_vec && b_vec && ctx->opt_gemm != 4) {
     MB_LAUNCH_P(ctx, MB_PROF_GEMM, (gemm_dmma_kernel<AK, BK, 4, true>), grid, 512, SMEM_BYTES, m, n, k, alpha, A, lda, B, ldb,
-                beta, C, ldc, lower_only ? 1 : 0, tn, nt, a_vec, b_vec, ksplit, kchunk, ws, ws_stride);
+                beta, C, ldc, lower_only ? 1 : 0, tn, nt, a_vec, b_vec, ksplit, kchunk, ws, ws_stride, ldw);
   } else {
     MB_LAUNCH_P(ctx, MB_PROF_GEMM, (gemm_dmma_kernel<AK, BK, 4, false>), grid, 512, SMEM_BYTES, m, n, k, alpha, A, lda, B, ldb,
-                beta, C, ldc, lower_only ? 1 : 0, tn, nt, a_vec, b_vec, ksplit, kchunk, ws, ws_stride);
+                beta, C, ldc, lower_only ? 1 : 0, tn, nt, a_vec, b_vec, ksplit, kchunk, ws, ws_stride, ldw);
   }
   if (ksplit > 1) {
     dim3 rgrid((unsigned)ceil_div64(n, 256), (unsigned)m);
-    MB_LAUNCH(ctx, splitk_reduce_kernel, rgrid, 256, 0, ws, ksplit, ws_stride, m, n, ldc, alpha, beta, C, lower_only ? 1 : 0);
+    MB_LAUNCH(ctx, splitk_reduce_kernel, rgrid, 256, 0, ws, ksplit, ws_stride, ldw, m, n, ldc, alpha, beta, C, lower_only ? 1 : 0);
   }
   return 0;
 }

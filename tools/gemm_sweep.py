@@ -10,7 +10,7 @@ ONLY = os.environ.get("SWEEP_ONLY")
 for variant in (0, 2, 4):
     be.set_option("gemm", variant)
     for (m, n, k) in [(128, 128, 16), (128, 128, 32), (128, 128, 64), (130, 257, 77), (130, 256, 77), (130, 256, 96), (130, 258, 64),
-                      (256, 256, 100), (64, 64, 33), (300, 66, 1000), (512, 384, 200)]:
+                      (256, 256, 100), (64, 64, 33), (300, 66, 1000), (512, 384, 200), (640, 640, 2100), (1300, 300, 4200), (200, 200, 9000)]:
         for ta in (0, 1):
             for tb in (0, 1):
                 if ONLY and ONLY != f"{variant}-{m}-{n}-{k}-{ta}-{tb}":
