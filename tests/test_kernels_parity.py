@@ -158,7 +158,8 @@ def test_potrf_reports_non_positive_definite(be):
     A = _spd(300, 1)
     A[200, 200] = -1.0
     info = be.potrf(be.upload(A))
-    assert 129 <= info <= 201
+    # the CUDA factorisation reports the failing pivot of the second 128-wide leaf; the NumPy test double only flags failure
+    assert (129 if be.name == "cuda" else 1) <= info <= 201
 
 
 @pytest.mark.parametrize("variant", [0, 1], ids=["inv128-gemm-leaves", "substitution-leaves"])

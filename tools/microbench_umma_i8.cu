@@ -62,6 +62,7 @@ umma_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ B, int N, i
   unsigned char* sA = smem;                 // [2 chunks][128 rows][16 B]
   unsigned char* sB = smem + 4096;          // [2 chunks][N rows][16 B]
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bars4[4];
   __shared__ uint32_t tmem_base_sh;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -69,6 +70,7 @@ umma_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ B, int N, i
   for (int e = tid; e < 128 * 32; e += 128) { const int r = e >> 5, k = e & 31; sA[(k >> 4) * (128 * 16) + r * 16 + (k & 15)] = A[e]; }
   for (int e = tid; e < N * 32; e += 128)   { const int r = e >> 5, k = e & 31; sB[(k >> 4) * (N * 16) + r * 16 + (k & 15)] = B[e]; }
   if (tid == 0) {
+    for (int q = 0; q < 4; q++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(s_u32(&bars4[q])));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(s_u32(&bar)));
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -89,7 +91,7 @@ umma_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ B, int N, i
 
   long long t0 = 0, t1 = 0;
   bool ok = true;
-  if (tid == 0) {
+  if (tid == 0 && mode < 2) {
     t0 = clock64();
     if (mode == 0) {
       umma_i8(tmem_base, da, db, idesc, 0);
@@ -103,6 +105,21 @@ umma_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ B, int N, i
     t1 = clock64();
     if (!ok) atomicExch(status, 1);
     if (mode == 1) cycles[blockIdx.x] = t1 - t0;
+  }
+  if (mode >= 2) {
+    // mode = 2 + log2(issuers): `issuers` warps each issue iters / issuers MMAs into their own TMEM column range
+    const int issuers = 1 << (mode - 2);
+    __syncthreads();
+    if (lane == 0 && warp < issuers) {
+      const int per = 512 / issuers, groups = per / N > 0 ? per / N : 1;
+      const long long s0 = clock64();
+      for (int it = 0; it < iters / issuers; it++)
+        umma_i8(tmem_base + (uint32_t)(warp * per + (it % groups) * N), da, db, idesc, it >= groups);
+      umma_commit(&bars4[warp]);
+      const bool done = mbar_wait_bounded(&bars4[warp], 0, 4000000000LL);
+      if (!done) atomicExch(status, 1);
+      if (warp == 0) cycles[blockIdx.x] = clock64() - s0;
+    }
   }
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -175,6 +192,18 @@ int main() {
       const double macs_per_mma = 128.0 * N * 32.0;
       printf("throughput N=%3d on %3d SM(s): %s %.1f clk per MMA, %.0f int8 MAC/clk/SM, kernel %.3f ms => %.1f TOPS (2 ops per MAC) chip-wide\n",
              N, grid, st ? "TIMEOUT" : "", avg / iters, macs_per_mma * iters / avg, ms, 2.0 * macs_per_mma * iters * grid / (ms * 1e-3) * 1e-12);
+    }
+  }
+  for (int N : {32, 64, 128}) {
+    for (int lg : {0, 1, 2}) {
+      CK(cudaMemset(status, 0, 4));
+      umma_kernel<<<sm, 128, 16384>>>(A, B, N, 2 + lg, iters, out, cyc, status);
+      CK(cudaDeviceSynchronize());
+      int st; CK(cudaMemcpy(&st, status, 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(hc, cyc, sizeof(long long) * sm, cudaMemcpyDeviceToHost));
+      double avg = 0; for (int i = 0; i < sm; i++) avg += (double)hc[i]; avg /= sm;
+      printf("multi-issuer N=%3d, %d issuing warps: %s %.1f clk per MMA (SM aggregate), %.0f int8 MAC/clk/SM\n", N, 1 << lg,
+             st ? "TIMEOUT" : "", avg / iters, 128.0 * N * 32.0 * iters / avg);
     }
   }
   return 0;
