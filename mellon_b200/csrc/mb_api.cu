@@ -59,6 +59,11 @@ void mb_cache_flush(mb_ctx* c) {
   c->cached_bytes = 0;
 }
 
+void mb_invalidate_graphs(mb_ctx* c) {
+  for (auto& kv : c->potrf_graphs) cudaGraphExecDestroy(kv.second.first);
+  c->potrf_graphs.clear();
+}
+
 cudaError_t mb_dev_malloc(mb_ctx* c, void** p, size_t bytes) {
   cudaError_t e = cudaMalloc(p, bytes);
   if (e != cudaSuccess && !c->block_cache.empty()) {
@@ -79,6 +84,9 @@ extern "C" int mb_ctx_destroy(mb_ctx* c) {
   if (c->flush_buf) cudaFree(c->flush_buf);
   if (c->gemm_ws) cudaFree(c->gemm_ws);
   if (c->trsm_ws) cudaFree(c->trsm_ws);
+  mb_invalidate_graphs(c);
+  if (c->potrf_buf) cudaFree(c->potrf_buf);
+  if (c->potrf_info) cudaFree(c->potrf_info);
   if (c->pinned) cudaFreeHost(c->pinned);
   prof_resolve(c);
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
@@ -191,6 +199,7 @@ extern "C" int mb_set_option(mb_ctx* c, const char* key, int value) {
   if (!strcmp(key, "gemm")) c->opt_gemm = value;
   else if (!strcmp(key, "cov")) c->opt_cov = value;
   else if (!strcmp(key, "trsm")) c->opt_trsm = value;
+  else if (!strcmp(key, "graph")) c->opt_graph = value;
   else if (!strcmp(key, "lossgrad")) c->opt_lossgrad = value;
   else MB_CHECK(false, "mb_set_option: unknown key %s", key);
   return 0;

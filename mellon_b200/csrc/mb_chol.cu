@@ -234,6 +234,10 @@ int trsm_left_rec(mb_ctx* ctx, const double* L, int64_t ldl, int64_t r0, int64_t
   return trsm_left_rec(ctx, L, ldl, r0, w1, trans, B, ldb, nrhs);
 }
 
+__global__ void merge_info_kernel(const int* from, int* to) {
+  if (*from != 0) atomicCAS(to, 0, *from);
+}
+
 __global__ void zero_upper_kernel(double* a, int64_t n, int64_t lda) {
   int64_t i = blockIdx.y, j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n && j < n && j > i) a[i * lda + j] = 0.0;
@@ -316,19 +320,33 @@ potrf_inv_leaf128_kernel(double* __restrict__ A, int64_t lda, int w, int64_t glo
   __syncthreads();
   for (int j = 0; j < w; j++) {
     // S[j][j] is final after the previous column's update and is not written during this column
-    double d = Ssh[j * ILD + j];
-    if (!(d > 0.0)) {
+    const double djj = Ssh[j * ILD + j];
+    double dinv, d;
+    if (!(djj > 0.0)) {
       if (tid == 0) atomicCAS(info, 0, (int)(global_off + j + 1));
-      d = nan("");
+      dinv = d = nan("");
+    } else {
+      dinv = rsqrt(djj);   // one reciprocal square root per column instead of a square root and 127 divisions
+      d = djj * dinv;
     }
-    d = sqrt(d);
-    if (q == 0 && i > j && i < w) Ssh[i * ILD + j] = Ssh[i * ILD + j] / d;
+    if (q == 0 && i > j && i < w) Ssh[i * ILD + j] *= dinv;
     if (tid == 0) rdiag[j] = d;  // the pivot itself is parked here until the loop is over
     __syncthreads();
     if (i > j && i < w) {
       const double lij = Ssh[i * ILD + j];
       double* row = Ssh + i * ILD;
-      for (int k = j + 1 + q; k <= i; k += IBT / IB) row[k] = fma(-lij, Ssh[k * ILD + j], row[k]);
+      const double* col = Ssh + j;
+      int k = j + 1 + q;
+      for (; k + 3 * (IBT / IB) <= i; k += 4 * (IBT / IB)) {  // four independent read-modify-writes in flight
+        const int k1 = k + IBT / IB, k2 = k + 2 * (IBT / IB), k3 = k + 3 * (IBT / IB);
+        const double a0 = row[k], a1 = row[k1], a2 = row[k2], a3 = row[k3];
+        const double b0 = col[k * ILD], b1 = col[k1 * ILD], b2 = col[k2 * ILD], b3 = col[k3 * ILD];
+        row[k] = fma(-lij, b0, a0);
+        row[k1] = fma(-lij, b1, a1);
+        row[k2] = fma(-lij, b2, a2);
+        row[k3] = fma(-lij, b3, a3);
+      }
+      for (; k <= i; k += IBT / IB) row[k] = fma(-lij, col[k * ILD], row[k]);
     }
     __syncthreads();
   }
@@ -363,6 +381,7 @@ int mb_trsm_ws(mb_ctx* ctx, int64_t m) {
   const size_t need = (size_t)ceil_div64(m, IB) * IB * IB * sizeof(double);
   if (need > ctx->trsm_ws_bytes) {
     MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    mb_invalidate_graphs(ctx);
     if (ctx->trsm_ws) MB_CUDA(cudaFree(ctx->trsm_ws));
     ctx->trsm_ws = nullptr;
     ctx->trsm_ws_bytes = 0;
@@ -449,7 +468,8 @@ int mb_trsm_right_lt_raw(mb_ctx* ctx, const double* Lp, int64_t ldl, int64_t m, 
   return trsm_inv_rec(ctx, Lp, ldl, ctx->trsm_ws, 0, m, X, ldx, nrows);
 }
 
-int mb_potrf_raw(mb_ctx* ctx, double* A, int64_t n, int64_t lda, int* info_dev) {
+// direct (stream) Cholesky of the n x n matrix at A; the strict upper triangle is zeroed
+static int potrf_direct(mb_ctx* ctx, double* A, int64_t n, int64_t lda, int* info_dev) {
   if (ctx->opt_trsm == 1 || n <= 32) {
     MB_TRY(potrf_rec(ctx, A, lda, 0, n, info_dev));
   } else {
@@ -463,6 +483,71 @@ int mb_potrf_raw(mb_ctx* ctx, double* A, int64_t n, int64_t lda, int* info_dev) 
     MB_LAUNCH(ctx, zero_upper_kernel, grid, 256, 0, A, n, lda);
   }
   return 0;
+}
+
+// The recursive factorisation is ~300 small dependent launches (22 ms for n = 5000, about half of it launch
+// gaps) and it is replicated on every rank, so it is the Amdahl term of the multi-GPU fit.  For n >= 1024 the
+// whole launch sequence is captured ONCE per size into a CUDA graph that works on context-owned buffers
+// (matrix copied in and out: 2 x 200 MB, 0.1 ms) and replayed on every later call.
+static int potrf_graph(mb_ctx* ctx, double* A, int64_t n, int64_t lda, int* info_dev, bool* done) {
+  *done = false;
+  const size_t bytes = (size_t)n * n * sizeof(double);
+  if (bytes > ctx->potrf_buf_bytes) {
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    mb_invalidate_graphs(ctx);  // they point into the old buffer
+    if (ctx->potrf_buf) MB_CUDA(cudaFree(ctx->potrf_buf));
+    ctx->potrf_buf = nullptr;
+    ctx->potrf_buf_bytes = 0;
+    MB_CUDA(mb_dev_malloc(ctx, (void**)&ctx->potrf_buf, bytes));
+    ctx->potrf_buf_bytes = bytes;
+  }
+  if (!ctx->potrf_info) MB_CUDA(mb_dev_malloc(ctx, (void**)&ctx->potrf_info, 256));
+  auto it = ctx->potrf_graphs.find(n);
+  if (it == ctx->potrf_graphs.end()) {
+    // everything that allocates or synchronises happens before the capture starts
+    MB_TRY(mb_trsm_ws(ctx, n));
+    const int64_t half = ((n / 2 + IB - 1) / IB) * IB + IB;
+    MB_TRY(mb_gemm_reserve_ws(ctx, (size_t)16 * half * (half + 2) * sizeof(double)));
+    const bool prof = ctx->prof_on;
+    ctx->prof_on = false;  // event pairs around captured launches would not be timeable
+    const int64_t launches0 = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+    int rc = (e == cudaSuccess) ? potrf_direct(ctx, ctx->potrf_buf, n, n, ctx->potrf_info) : -1;
+    cudaError_t e2 = (e == cudaSuccess) ? cudaStreamEndCapture(ctx->stream, &graph) : e;
+    ctx->prof_on = prof;
+    const int64_t nodes = ctx->launches - launches0;
+    ctx->launches = launches0;
+    cudaGraphExec_t exec = nullptr;
+    if (rc != 0 || e2 != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      ctx->opt_graph = 0;  // fall back to stream launches for the rest of this context's life
+      return 0;
+    }
+    cudaGraphDestroy(graph);
+    it = ctx->potrf_graphs.emplace(n, std::make_pair(exec, nodes)).first;
+  }
+  MB_CUDA(cudaMemcpy2DAsync(ctx->potrf_buf, (size_t)n * sizeof(double), A, (size_t)lda * sizeof(double),
+                            (size_t)n * sizeof(double), (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+  MB_CUDA(cudaMemsetAsync(ctx->potrf_info, 0, sizeof(int), ctx->stream));
+  MB_CUDA(cudaGraphLaunch(it->second.first, ctx->stream));
+  ctx->launches += it->second.second;
+  MB_CUDA(cudaMemcpy2DAsync(A, (size_t)lda * sizeof(double), ctx->potrf_buf, (size_t)n * sizeof(double),
+                            (size_t)n * sizeof(double), (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+  // a non-positive pivot found by the replay is OR-ed into the caller's flag (first failing pivot wins there)
+  MB_LAUNCH(ctx, merge_info_kernel, 1, 1, 0, ctx->potrf_info, info_dev);
+  *done = true;
+  return 0;
+}
+
+int mb_potrf_raw(mb_ctx* ctx, double* A, int64_t n, int64_t lda, int* info_dev) {
+  if (ctx->opt_graph && ctx->opt_trsm != 1 && n >= 1024) {
+    bool done = false;
+    MB_TRY(potrf_graph(ctx, A, n, lda, info_dev, &done));
+    if (done) return 0;
+  }
+  return potrf_direct(ctx, A, n, lda, info_dev);
 }
 
 extern "C" int mb_potrf(mb_ctx* ctx, mb_mat* a) {

@@ -48,6 +48,12 @@ struct mb_ctx {
   // same size class, so a fit does not pay cudaMalloc / cudaFree of its 40 GB factor every time
   std::multimap<size_t, double*> block_cache;
   size_t cached_bytes = 0, cache_cap = 0;
+  // CUDA-graph replay of the launch-bound Cholesky (fixed internal buffers so one graph per size serves every call)
+  double* potrf_buf = nullptr;
+  size_t potrf_buf_bytes = 0;
+  int* potrf_info = nullptr;
+  std::map<int64_t, std::pair<cudaGraphExec_t, int64_t>> potrf_graphs;  // n -> (exec, kernel nodes)
+  int opt_graph = 1;     // 1 = replay the Cholesky (n >= 1024) from a captured graph
   double* trsm_ws = nullptr;           // inverted 128 x 128 diagonal blocks of the TRSM
   size_t trsm_ws_bytes = 0;
   double* gemm_ws = nullptr;           // split-k partial tiles (own buffer: GEMMs run inside scratch users)
@@ -149,6 +155,8 @@ int mb_potrf_raw(mb_ctx* ctx, double* A, int64_t n, int64_t lda, int* info_dev_a
 int mb_trsm_right_lt_raw(mb_ctx* ctx, const double* Lp, int64_t ldl, int64_t m, double* X,
                          int64_t ldx, int64_t nrows);
 int mb_allreduce_raw(mb_ctx* ctx, double* p, int64_t count);
+void mb_invalidate_graphs(mb_ctx* ctx);  // captured graphs hold raw workspace pointers: drop them when one moves
+int mb_gemm_reserve_ws(mb_ctx* ctx, size_t bytes);  // grow the split-k workspace up front (no cudaMalloc under capture)
 
 // warp / block reductions -------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

@@ -406,15 +406,7 @@ int launch_gemm(mb_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, cons
     ksplit = (int)ceil_div64(k, kchunk);
     ldw = (n + 1) & ~(int64_t)1;  // dense, even (16-byte rows)
     ws_stride = m * ldw;
-    const size_t need = (size_t)ksplit * ws_stride * sizeof(double);
-    if (need > ctx->gemm_ws_bytes) {
-      MB_CUDA(cudaStreamSynchronize(ctx->stream));
-      if (ctx->gemm_ws) MB_CUDA(cudaFree(ctx->gemm_ws));
-      ctx->gemm_ws = nullptr;
-      ctx->gemm_ws_bytes = 0;
-      MB_CUDA(mb_dev_malloc(ctx, (void**)&ctx->gemm_ws, need));
-      ctx->gemm_ws_bytes = need;
-    }
+    MB_TRY(mb_gemm_reserve_ws(ctx, (size_t)ksplit * ws_stride * sizeof(double)));
     ws = ctx->gemm_ws;
   }
   int grid = (int)min(nt * ksplit, (int64_t)ctx->n_sm);
@@ -439,6 +431,19 @@ int launch_gemm(mb_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, cons
 }
 
 }  // namespace
+
+int mb_gemm_reserve_ws(mb_ctx* ctx, size_t need) {
+  if (need > ctx->gemm_ws_bytes) {
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    mb_invalidate_graphs(ctx);
+    if (ctx->gemm_ws) MB_CUDA(cudaFree(ctx->gemm_ws));
+    ctx->gemm_ws = nullptr;
+    ctx->gemm_ws_bytes = 0;
+    MB_CUDA(mb_dev_malloc(ctx, (void**)&ctx->gemm_ws, need));
+    ctx->gemm_ws_bytes = need;
+  }
+  return 0;
+}
 
 int mb_gemm_raw(mb_ctx* ctx, bool a_kmajor, bool b_kmajor, int64_t m, int64_t n, int64_t k, double alpha,
                 const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,

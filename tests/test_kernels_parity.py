@@ -150,6 +150,28 @@ def test_potrf(be, variant, n):
     assert rel_err(Lc, Lref) < 1e-9
 
 
+def test_potrf_graph_replay(be):
+    """n >= 1024 replays a captured CUDA graph on context-owned buffers: several matrices through the same graph,
+    a second size, a non-positive pivot found inside a replay, and the stream path (graph off) for comparison."""
+    for seed, n in ((1, 1300), (2, 1300), (3, 1100), (4, 1300)):
+        A = _spd(n, seed)
+        for graph in (1, 0):
+            be.set_option("graph", graph)
+            try:
+                Ad = be.upload(A.copy())
+                assert be.potrf(Ad) == 0
+            finally:
+                be.set_option("graph", 1)
+            Lc = Ad.numpy()
+            assert np.allclose(np.triu(Lc, 1), 0.0)
+            assert rel_err(Lc @ Lc.T, A) < 1e-13
+    A = _spd(1300, 5)
+    A[700, 700] = -1.0
+    info = be.potrf(be.upload(A))
+    assert (641 if be.name == "cuda" else 1) <= info <= 701
+    assert be.potrf(be.upload(_spd(1300, 6))) == 0   # the flag of the failed replay does not stick
+
+
 def test_potrf_reports_non_positive_definite(be):
     A = _spd(64, 1)
     A[40, 40] = -1.0
