@@ -304,60 +304,173 @@ trsv_kernel(const double* __restrict__ L, int64_t ldl, int m, double* __restrict
 
 
 // ---- leaf: Cholesky of one (w <= 128) diagonal block in shared memory + the inverse of its factor -----
-// 1024 threads: thread (i = tid & 127, q = tid >> 7) updates columns k = j + 1 + q (mod 8) of row i in the
-// rank-1 update of column j; two barriers per column.  The factor goes back to A, its inverse to `inv_out`.
-__global__ void __launch_bounds__(IBT)
+// Blocked inside the CTA on 32 x 32 sub-blocks (1024 threads, 12 + 10 barriers instead of 256):
+//   factor, per 32-column panel p: (A1) warp 0 factors the diagonal block left-looking, its row in registers and
+//   the finished rows broadcast from shared memory; (A2) one thread per row below solves its 32 entries against
+//   that block; (A3) all threads apply the rank-32 update to the trailing sub-matrix.
+//   inverse: (B1) warps 0..3 invert the four diagonal blocks (lane = column, forward substitution in registers);
+//   (B2) block row by block row X_ij = -X_ii (sum_k L_ik X_kj), one thread per entry; finished off-diagonal
+//   blocks are parked TRANSPOSED in the (otherwise zero) strict upper part of the shared-memory tile.
+// Rows / columns >= w are padded with the identity, so every loop is uniform; only the w x w part is stored.
+constexpr int SB = 32, LT = 512;  // 512 threads: 128 registers each (the 32-entry rows live in registers)
+
+__global__ void __launch_bounds__(LT)
 potrf_inv_leaf128_kernel(double* __restrict__ A, int64_t lda, int w, int64_t global_off, int* info,
                          double* __restrict__ inv_out) {
   extern __shared__ double Ssh[];
-  double* xw = Ssh + IB * ILD;
-  double* rdiag = xw + (IBT / 32) * IB;
-  const int tid = threadIdx.x, i = tid & (IB - 1), q = tid >> 7;
-  for (int e = tid; e < IB * IB; e += IBT) {
+  double* xdiag = Ssh + IB * ILD;            // 4 x (32 x 32): inverses of the diagonal sub-blocks
+  double* rdiag = xdiag + (IBT / 32) * IB;   // 128 reciprocals of the factor's diagonal
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < IB * IB; e += LT) {
     const int r = e / IB, k = e % IB;
-    Ssh[r * ILD + k] = (r < w && k <= r) ? A[(int64_t)r * lda + k] : 0.0;
+    double v = 0.0;
+    if (r < w && k <= r) v = A[(int64_t)r * lda + k];
+    else if (r >= w && k == r) v = 1.0;
+    Ssh[r * ILD + k] = v;
   }
   __syncthreads();
-  for (int j = 0; j < w; j++) {
-    // S[j][j] is final after the previous column's update and is not written during this column
-    const double djj = Ssh[j * ILD + j];
-    double dinv, d;
-    if (!(djj > 0.0)) {
-      if (tid == 0) atomicCAS(info, 0, (int)(global_off + j + 1));
-      dinv = d = nan("");
-    } else {
-      dinv = rsqrt(djj);   // one reciprocal square root per column instead of a square root and 127 divisions
-      d = djj * dinv;
-    }
-    if (q == 0 && i > j && i < w) Ssh[i * ILD + j] *= dinv;
-    if (tid == 0) rdiag[j] = d;  // the pivot itself is parked here until the loop is over
-    __syncthreads();
-    if (i > j && i < w) {
-      const double lij = Ssh[i * ILD + j];
-      double* row = Ssh + i * ILD;
-      const double* col = Ssh + j;
-      int k = j + 1 + q;
-      for (; k + 3 * (IBT / IB) <= i; k += 4 * (IBT / IB)) {  // four independent read-modify-writes in flight
-        const int k1 = k + IBT / IB, k2 = k + 2 * (IBT / IB), k3 = k + 3 * (IBT / IB);
-        const double a0 = row[k], a1 = row[k1], a2 = row[k2], a3 = row[k3];
-        const double b0 = col[k * ILD], b1 = col[k1 * ILD], b2 = col[k2 * ILD], b3 = col[k3 * ILD];
-        row[k] = fma(-lij, b0, a0);
-        row[k1] = fma(-lij, b1, a1);
-        row[k2] = fma(-lij, b2, a2);
-        row[k3] = fma(-lij, b3, a3);
+
+  for (int p = 0; p < IB / SB; p++) {
+    const int c0 = p * SB;
+    // (A1) diagonal block, warp 0, lane = row
+    if (warp == 0) {
+      double row[SB];
+#pragma unroll
+      for (int k = 0; k < SB; k++) row[k] = Ssh[(c0 + lane) * ILD + c0 + k];
+#pragma unroll
+      for (int j = 0; j < SB; j++) {
+        double s = row[j];
+#pragma unroll
+        for (int k = 0; k < j; k++) s = fma(-row[k], Ssh[(c0 + j) * ILD + c0 + k], s);  // finished row j, broadcast
+        const double djj = __shfl_sync(0xffffffffu, s, j);
+        double dinv, d;
+        if (!(djj > 0.0)) {
+          if (lane == 0 && c0 + j < w) atomicCAS(info, 0, (int)(global_off + c0 + j + 1));
+          dinv = d = nan("");
+        } else {
+          dinv = rsqrt(djj);
+          d = djj * dinv;
+        }
+        const double v = (lane == j) ? d : s * dinv;
+        row[j] = v;
+        if (lane >= j) Ssh[(c0 + lane) * ILD + c0 + j] = v;
+        if (lane == j) rdiag[c0 + j] = dinv;
+        __syncwarp();
       }
-      for (; k <= i; k += IBT / IB) row[k] = fma(-lij, col[k * ILD], row[k]);
+    }
+    __syncthreads();
+    // (A2) rows below the diagonal block: X[r][0..31] = S[r][c0..] D^-T, one thread per row
+    if (tid < IB - c0 - SB) {
+      const int r = c0 + SB + tid;
+      double x[SB];
+#pragma unroll
+      for (int c = 0; c < SB; c++) x[c] = Ssh[r * ILD + c0 + c];
+#pragma unroll
+      for (int c = 0; c < SB; c++) {
+        double s = x[c];
+#pragma unroll
+        for (int k = 0; k < c; k++) s = fma(-x[k], Ssh[(c0 + c) * ILD + c0 + k], s);
+        x[c] = s * rdiag[c0 + c];
+      }
+#pragma unroll
+      for (int c = 0; c < SB; c++) Ssh[r * ILD + c0 + c] = x[c];
+    }
+    __syncthreads();
+    // (A3) trailing update S[i][k] -= sum_c X[i][c] X[k][c] for c0 + 32 <= k <= i
+    const int t0 = c0 + SB, nt = IB - t0;
+    for (int e = tid; e < nt * nt; e += LT) {
+      const int i = t0 + e / nt, k = t0 + e % nt;
+      if (k <= i) {
+        double s = Ssh[i * ILD + k];
+#pragma unroll 8
+        for (int c = 0; c < SB; c++) s = fma(-Ssh[i * ILD + c0 + c], Ssh[k * ILD + c0 + c], s);
+        Ssh[i * ILD + k] = s;
+      }
     }
     __syncthreads();
   }
-  if (tid < w) Ssh[tid * ILD + tid] = rdiag[tid];
-  __syncthreads();
-  for (int e = tid; e < IB * IB; e += IBT) {
+  // the factor goes back to global memory (explicit zeros above the diagonal)
+  for (int e = tid; e < IB * IB; e += LT) {
     const int r = e / IB, k = e % IB;
     if (r < w && k < w) A[(int64_t)r * lda + k] = (k <= r) ? Ssh[r * ILD + k] : 0.0;
   }
+  // (B1) inverses of the four diagonal sub-blocks: warp p, lane = column
+  if (warp < IB / SB) {
+    const int c0 = warp * SB;
+    double x[SB];
+#pragma unroll
+    for (int r = 0; r < SB; r++) {
+      double s = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < r; k++) s = fma(-Ssh[(c0 + r) * ILD + c0 + k], x[k], s);  // x[k] = 0 above the lane's column
+      x[r] = (r >= lane) ? s * rdiag[c0 + r] : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < SB; r++) xdiag[warp * SB * SB + r * SB + lane] = x[r];
+  }
   __syncthreads();
-  tri_inv_block(Ssh, xw, rdiag, w, inv_out);
+  // (B2) off-diagonal blocks, block row i: X_ij = -X_ii (sum_{k=j}^{i-1} L_ik X_kj); each thread owns the two
+  // entries (a, bcol) and (a + 16, bcol) of every 32 x 32 block
+  const int bcol = tid & 31;
+  for (int i = 1; i < IB / SB; i++) {
+    double wv[2][IB / SB - 1];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int a = (tid >> 5) + 16 * h;
+#pragma unroll
+      for (int j = 0; j < IB / SB - 1; j++) {
+        wv[h][j] = 0.0;
+        if (j < i) {
+          double s = 0.0;
+          for (int k = j; k < i; k++) {
+#pragma unroll 8
+            for (int c = 0; c < SB; c++) {
+              const double xkj = (k == j) ? xdiag[j * SB * SB + c * SB + bcol]
+                                          : Ssh[(SB * j + bcol) * ILD + SB * k + c];  // X_kj[c][bcol], parked transposed
+              s = fma(Ssh[(SB * i + a) * ILD + SB * k + c], xkj, s);
+            }
+          }
+          wv[h][j] = s;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+      for (int j = 0; j < IB / SB - 1; j++)
+        if (j < i) Ssh[(SB * j + bcol) * ILD + SB * i + (tid >> 5) + 16 * h] = wv[h][j];  // W_ij[a][bcol] parked transposed
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int a = (tid >> 5) + 16 * h;
+#pragma unroll
+      for (int j = 0; j < IB / SB - 1; j++) {
+        if (j < i) {
+          double s = 0.0;
+          for (int c = 0; c <= a; c++) s = fma(xdiag[i * SB * SB + a * SB + c], Ssh[(SB * j + bcol) * ILD + SB * i + c], s);
+          wv[h][j] = -s;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+      for (int j = 0; j < IB / SB - 1; j++)
+        if (j < i) Ssh[(SB * j + bcol) * ILD + SB * i + (tid >> 5) + 16 * h] = wv[h][j];  // X_ij[a][bcol]
+    __syncthreads();
+  }
+  // (B3) dense 128 x 128 inverse (zero above the diagonal and beyond w)
+  for (int e = tid; e < IB * IB; e += LT) {
+    const int r = e / IB, c = e % IB;
+    double v = 0.0;
+    if (r < w && c < w && c <= r) {
+      const int bi = r / SB, bj = c / SB;
+      v = (bi == bj) ? xdiag[bi * SB * SB + (r % SB) * SB + (c % SB)] : Ssh[c * ILD + r];
+    }
+    inv_out[(int64_t)r * IB + c] = v;
+  }
 }
 
 // recursive Cholesky with 128-wide leaves; panel solves run as GEMMs on the inverted leaf factors
@@ -365,7 +478,7 @@ int potrf128_rec(mb_ctx* ctx, double* A, int64_t lda, int64_t off, int64_t n, in
   if (n <= 0) return 0;
   double* D = A + off * lda + off;
   if (n <= IB) {
-    MB_LAUNCH(ctx, potrf_inv_leaf128_kernel, 1, IBT, IB_SMEM, D, lda, (int)n, off, info, inv + (off / IB) * IB * IB);
+    MB_LAUNCH(ctx, potrf_inv_leaf128_kernel, 1, LT, IB_SMEM, D, lda, (int)n, off, info, inv + (off / IB) * IB * IB);
     return 0;
   }
   const int64_t n1 = ((n / 2 + IB - 1) / IB) * IB, n2 = n - n1;

@@ -61,8 +61,9 @@ def _nn_constants(nn_distances, d):
     r = np.asarray(nn_distances, dtype=float)
     d = np.asarray(d, dtype=float) if np.ndim(d) else float(d)
     const = (d * np.log(np.pi) / 2) - gammaln(d / 2 + 1)
-    V = np.log(r) * d + const
-    Vdr = np.log(d) + ((d - 1) * np.log(r)) + const
+    log_r = np.log(r)  # one pass over the N distances (the reference evaluates log r twice)
+    V = log_r * d + const
+    Vdr = np.log(d) + ((d - 1) * log_r) + const
     return V, Vdr
 
 
