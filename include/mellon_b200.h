@@ -101,7 +101,12 @@ int mb_prof_reset(mb_ctx* ctx);
 int mb_prof_read(mb_ctx* ctx, int cls, int64_t* count, double* ms, double* work);
 /* overwrite a scratch buffer larger than L2 (cache flush between timed iterations) */
 int mb_flush_l2(mb_ctx* ctx);
-/* select kernel variants for A/B measurements ("gemm", "cov", "lossgrad") */
+/* select kernel variants for A/B measurements and parity tests (0 is always the default path):
+ *   "cov"      1 = DFMA register-tile covariance kernel, 2 = general (multi-leaf) kernel
+ *   "gemm"     1 = DFMA reference GEMM, 2 = 8-warp DMMA tiles, 3 = no split-k, 4 = generic operand loaders
+ *   "trsm"     1 = 32-wide substitution leaves for TRSM / Cholesky (no inverted 128-blocks, no blocked TRSV)
+ *   "lossgrad" 1 = two-pass objective, 2 = register-fused single pass (0 = bulk-TMA ring)
+ *   "graph"    0 = launch the Cholesky on the stream instead of replaying its CUDA graph */
 int mb_set_option(mb_ctx* ctx, const char* key, int value);
 
 /* pinned (page-locked) host buffers, so uploads / the streaming predictor overlap with compute */
