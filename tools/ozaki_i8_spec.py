@@ -78,13 +78,14 @@ def report(name, x, y, c=1.0):
     return sq
 
 
-D = 50
-x = rng.random((256, D)); y = rng.random((192, D))
-report("uniform [0,1)^50 (bench workload)", x, y, c=np.sqrt(5.0) / 38.0)
-report("standard normal", rng.standard_normal((256, D)), rng.standard_normal((192, D)))
-report("wide dynamic range (columns scaled 1e-6..1e3)", rng.standard_normal((256, D)) * np.logspace(-6, 3, D), rng.standard_normal((192, D)) * np.logspace(-6, 3, D))
-report("one dominant coordinate per row", np.eye(D)[rng.integers(0, D, 256)] * 100 + rng.standard_normal((256, D)) * 1e-3, rng.standard_normal((192, D)))
-# coincident points: squared distance must stay at rounding level of the norms (then + 1e-12 c^2 takes over)
-xs = rng.random((64, D)) * 40.0
-sq = report("coincident rows, |x|^2 ~ 2.7e4", xs, xs)
-print(f"coincident points: max |sq_ii| = {np.max(np.abs(np.diag(sq))):.2e} (float64 expansion form: ~{np.finfo(float).eps * 2.7e4 * 4:.1e})")
+if __name__ == "__main__":
+    D = 50
+    x = rng.random((256, D)); y = rng.random((192, D))
+    report("uniform [0,1)^50 (bench workload)", x, y, c=np.sqrt(5.0) / 38.0)
+    report("standard normal", rng.standard_normal((256, D)), rng.standard_normal((192, D)))
+    report("wide dynamic range (columns scaled 1e-6..1e3)", rng.standard_normal((256, D)) * np.logspace(-6, 3, D), rng.standard_normal((192, D)) * np.logspace(-6, 3, D))
+    report("one dominant coordinate per row", np.eye(D)[rng.integers(0, D, 256)] * 100 + rng.standard_normal((256, D)) * 1e-3, rng.standard_normal((192, D)))
+    # coincident points: squared distance must stay at rounding level of the norms (then + 1e-12 c^2 takes over)
+    xs = rng.random((64, D)) * 40.0
+    sq = report("coincident rows, |x|^2 ~ 2.7e4", xs, xs)
+    print(f"coincident points: max |sq_ii| = {np.max(np.abs(np.diag(sq))):.2e} (float64 expansion form: ~{np.finfo(float).eps * 2.7e4 * 4:.1e})")
