@@ -226,6 +226,8 @@ def test_gemm(be, ta, tb, m, n, k):
 @pytest.mark.parametrize("variant", [0, 1, 2, 3], ids=["dmma16w", "dfma", "dmma8w", "nosplit"])
 @pytest.mark.parametrize("n,r", [(1, 1), (50, 7), (1000, 64), (777, 130), (3000, 257), (20000, 1500)])
 def test_gram_and_ridge(be, variant, n, r):
+    if n >= 20000 and variant in (1, 2):
+        pytest.skip("the large split-k case is for the default kernel and its no-split twin")
     rng = np.random.default_rng(n + r)
     L = rng.standard_normal((n, r)) / np.sqrt(r)
     t = rng.standard_normal(n)
@@ -247,6 +249,8 @@ def test_gram_and_ridge(be, variant, n, r):
 @pytest.mark.parametrize("n,r", [(1, 1), (9, 4), (3, 2), (1000, 64), (513, 33), (2000, 1000), (300, 2050), (4000, 5000),
                                  (5000, 2000), (777, 5000), (20011, 5000), (100, 8192), (64, 9000)])
 def test_loss_grad_hess_transform(be, variant, n, r):
+    if n >= 20000 and variant != 0:
+        pytest.skip("the 800 MB case is for the default (bulk-TMA ring) kernel")
     rng = np.random.default_rng(n * 3 + r)
     L = rng.standard_normal((n, r)) / np.sqrt(r)
     nn = rng.random(n) * 0.5 + 0.05
