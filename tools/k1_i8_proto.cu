@@ -27,6 +27,7 @@ constexpr int D = 50, KP = 64, NS = 8, TB = 128;           // features, padded k
 constexpr int SLICE_BYTES = 4 * TB * 16;                   // one slice of one 128-row block: [4 chunks][128 rows][16 B]
 constexpr int BLOCK_BYTES = NS * SLICE_BYTES;              // 64 KB
 constexpr int NT = 512;
+constexpr int SMEM_TOTAL = 3 * BLOCK_BYTES + (NT / 32) * 32 * 8 * 8;   // operands + per-warp output staging strips (2 KB each)
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ const double g_tab[64] = MB_EXP2_TABLE_INIT;
@@ -107,7 +108,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t* v) {
 __global__ void __launch_bounds__(NT, 1)
 k1_i8_kernel(const int8_t* __restrict__ xd, const double* __restrict__ xn, const double* __restrict__ xs, int64_t n,
              const int8_t* __restrict__ yd, const double* __restrict__ yn, const double* __restrict__ ys, int64_t m,
-             double eps_scaled, double* __restrict__ out, int* __restrict__ status) {
+             double eps_scaled, double* __restrict__ out, int* __restrict__ status, int mode) {
+  // mode bits (timing decomposition only): 1 = skip the sqrt/exp/polynomial of the final epilogue, 2 = no MMAs at all,
+  // 4 = no stores
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* sx = smem;                                 // 64 KB
   unsigned char* sy0 = smem + BLOCK_BYTES;                  // 2 x 64 KB
@@ -172,8 +175,10 @@ k1_i8_kernel(const int8_t* __restrict__ xd, const double* __restrict__ xn, const
     }
     umma_commit(&bar_m[issuer][b]);
   };
-  if (tid == 0) { issue(0, 0); issue(1, 0); }
-  if (tid == 32) { issue(0, 1); issue(1, 1); }
+  if (!(mode & 2)) {
+    if (tid == 0) { issue(0, 0); issue(1, 0); }
+    if (tid == 32) { issue(0, 1); issue(1, 1); }
+  }
 
   // epilogue mapping: TMEM lane quadrant = warp % 4 (rows), 32-column strip = warp / 4
   const int row = (warp & 3) * 32 + lane;
@@ -187,8 +192,10 @@ k1_i8_kernel(const int8_t* __restrict__ xd, const double* __restrict__ xn, const
       const int64_t S = jt * 4 + s;
       const int b = (int)(S & 1);
       const uint32_t par = (uint32_t)((S >> 1) & 1);
-      mbar_wait(&bar_m[0][b], par, status);
-      mbar_wait(&bar_m[1][b], par, status);
+      if (!(mode & 2)) {
+        mbar_wait(&bar_m[0][b], par, status);
+        mbar_wait(&bar_m[1][b], par, status);
+      }
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const uint32_t t_even = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(b * 256 + cstrip);
       const uint32_t t_odd = t_even + 128;
@@ -206,31 +213,46 @@ k1_i8_kernel(const int8_t* __restrict__ xd, const double* __restrict__ xn, const
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       __syncthreads();                       // every warp is done with accumulator buffer b
-      if (tid == 0) {
+      if (tid == 0 && !(mode & 2)) {
         if (s == 3 && jt + 2 < n_ytiles) {   // all MMAs that read landmark buffer jt & 1 have completed: refill it
           mbar_expect_tx(&bar_y[jt & 1], BLOCK_BYTES);
           bulk_g2s(sy0 + (jt & 1) * BLOCK_BYTES, yd + (jt + 2) * (int64_t)BLOCK_BYTES, BLOCK_BYTES, &bar_y[jt & 1]);
         }
         issue(S + 2, 0);
       }
-      if (tid == 32) issue(S + 2, 1);
+      if (tid == 32 && !(mode & 2)) issue(S + 2, 1);
     }
-    // Matern52 epilogue on the 32 elements of this thread: sq = xn + yn - 2 (S xs ys)
+    // Matern52 epilogue on the 32 elements of this thread: sq = xn + yn - 2 (S xs ys).  The thread owns one ROW of
+    // the tile (TMEM lane), so the results are transposed through a 2 KB per-warp staging strip, 8 columns at a
+    // time, and leave as 16-byte stores that cover 8 rows x 64 contiguous bytes per instruction.
     const int64_t col0 = jt * TB + cstrip;
-    double* o = out + grow * m + col0;
+    double* stage = reinterpret_cast<double*>(smem + 3 * BLOCK_BYTES) + warp * (32 * 8);   // [32 rows][8], column index XOR-swizzled by the row
+    double* obase = out + (panel * TB + (warp & 3) * 32) * m + col0;
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      double kv[2];
+    for (int j0 = 0; j0 < 32; j0 += 8) {
 #pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const double dot = acc[j + e] * xs_i * ys[col0 + j + e];
-        double sq = fma(-2.0, dot, xn_i + yn[col0 + j + e]);
+      for (int e = 0; e < 8; e++) {
+        const double dot = acc[j0 + e] * xs_i * ys[col0 + j0 + e];
+        double sq = fma(-2.0, dot, xn_i + yn[col0 + j0 + e]);
         sq = mbmath::clamp_tiny(sq);
-        const double r = mbmath::sqrt_pos(sq);
-        const double ex = mbmath::exp_neg(r, tab);
-        kv[e] = fma(fma(r, 1.0 / 3.0, 1.0), r, 1.0) * ex;
+        double kvv = sq;
+        if (!(mode & 1)) {
+          const double r = mbmath::sqrt_pos(sq);
+          const double ex = mbmath::exp_neg(r, tab);
+          kvv = fma(fma(r, 1.0 / 3.0, 1.0), r, 1.0) * ex;
+        }
+        stage[lane * 8 + (e ^ (lane & 7))] = kvv;
       }
-      *reinterpret_cast<double2*>(o + j) = make_double2(kv[0], kv[1]);
+      __syncwarp();
+      if (!(mode & 4)) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int rr = q * 8 + (lane >> 2), cc = (lane & 3) * 2;
+          const double v0 = stage[rr * 8 + (cc ^ (rr & 7))], v1 = stage[rr * 8 + ((cc + 1) ^ (rr & 7))];
+          *reinterpret_cast<double2*>(obase + (int64_t)rr * m + j0 + cc) = make_double2(v0, v1);
+        }
+      }
+      __syncwarp();
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -253,7 +275,7 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&xn, n * 8)); CK(cudaMalloc(&xs, n * 8)); CK(cudaMalloc(&yn, m * 8)); CK(cudaMalloc(&ys, m * 8));
   CK(cudaMalloc(&out, (size_t)n * m * 8)); CK(cudaMalloc(&status, 4)); CK(cudaMemset(status, 0, 4));
   CK(cudaMemcpy(x, hx.data(), hx.size() * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(y, hy.data(), hy.size() * 8, cudaMemcpyHostToDevice));
-  CK(cudaFuncSetAttribute(k1_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * BLOCK_BYTES));
+  CK(cudaFuncSetAttribute(k1_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
   cudaEvent_t e0, e1, e2; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
   float ms_pack = 0, ms_k = 1e30f;
   for (int rep = 0; rep < 3; rep++) {
@@ -261,7 +283,7 @@ int main(int argc, char** argv) {
     pack_kernel<<<(unsigned)((n + 127) / 128), 128>>>(x, n, c, xd, xn, xs, 1.0);
     pack_kernel<<<(unsigned)((m + 127) / 128), 128>>>(y, m, c, yd, yn, ys, ldexp(1.0, 49));   // 128^7 folded into the landmark scale
     CK(cudaEventRecord(e1));
-    k1_i8_kernel<<<(unsigned)(n / TB), NT, 3 * BLOCK_BYTES>>>(xd, xn, xs, n, yd, yn, ys, m, 1e-12 * c * c, out, status);
+    k1_i8_kernel<<<(unsigned)(n / TB), NT, SMEM_TOTAL>>>(xd, xn, xs, n, yd, yn, ys, m, 1e-12 * c * c, out, status, 0);
     CK(cudaEventRecord(e2)); CK(cudaEventSynchronize(e2));
     float a, b; CK(cudaEventElapsedTime(&a, e0, e1)); CK(cudaEventElapsedTime(&b, e1, e2));
     ms_pack = a; if (b < ms_k) ms_k = b;
@@ -291,5 +313,17 @@ int main(int argc, char** argv) {
   printf("pack %.3f ms, kernel %.3f ms => %.1f GB/s algorithmic (kernel only), %.1f GB/s with the pack pass\n", ms_pack, ms_k,
          bytes / ms_k * 1e-6, bytes / (ms_k + ms_pack) * 1e-6);
   printf("scaled to N=1e6, M=5000: kernel %.2f ms, pack %.2f ms\n", ms_k * (1e6 * 5000.0) / ((double)n * m), ms_pack * 1e6 / n);
+  // timing decomposition (results of these runs are not checked)
+  for (int mode = 1; mode <= 7; mode++) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 2; rep++) {
+      CK(cudaEventRecord(e1));
+      k1_i8_kernel<<<(unsigned)(n / TB), NT, SMEM_TOTAL>>>(xd, xn, xs, n, yd, yn, ys, m, 1e-12 * c * c, out, status, mode);
+      CK(cudaEventRecord(e2)); CK(cudaEventSynchronize(e2));
+      float b; CK(cudaEventElapsedTime(&b, e1, e2)); if (b < best) best = b;
+    }
+    printf("mode %d (%s%s%s): kernel %.3f ms\n", mode, (mode & 1) ? "no sqrt/exp/poly " : "", (mode & 2) ? "no MMAs " : "",
+           (mode & 4) ? "no stores" : "", best);
+  }
   return 0;
 }
