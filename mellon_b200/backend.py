@@ -295,14 +295,21 @@ class CudaBackend:
 
     # -- covariance programs --------------------------------------------------------------------
     def _prog(self, cov_func, n_cols):
+        """Compiled covariance program of ``cov_func``, cached per (object, width, STATE): covariances are
+        mutable (the reference's tests assign ``cov.active_dims`` after a first evaluation), so a cached program
+        is reused only while the serialised expression tree is unchanged."""
         from .base_cov import compile_covariance
 
+        try:
+            fingerprint = repr(cov_func.__getstate__())
+        except Exception:  # user-defined subclasses without serialisation: never cache
+            fingerprint = None
         key = (id(cov_func), int(n_cols))
         hit = self._progs.get(key)
-        if hit is not None and hit[0] is cov_func:
+        if hit is not None and hit[0] is cov_func and fingerprint is not None and hit[2] == fingerprint:
             return hit[1]
         prog = compile_covariance(cov_func, int(n_cols))
-        self._progs[key] = (cov_func, prog)
+        self._progs[key] = (cov_func, prog, fingerprint)
         return prog
 
     def supports(self, cov_func, n_cols):

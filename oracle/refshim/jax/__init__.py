@@ -62,7 +62,11 @@ def _complex_step_grad(fun, x):
     for i in range(flat.size):
         z = flat.astype(complex)
         z[i] += 1j * _H
-        g[i] = _np.imag(_np.asarray(fun(_as_array(z.reshape(x.shape))))) / _H
+        res = _np.asarray(fun(_as_array(z.reshape(x.shape))))
+        if not _np.iscomplexobj(res):
+            # the function drops the imaginary part (e.g. it evaluates on a float64 device): no complex step
+            raise TypeError("function is not complex-differentiable")
+        g[i] = _np.imag(res) / _H
     return g.reshape(x.shape)
 
 
@@ -133,7 +137,14 @@ def _jac(fun, x):
             e[i] = 1.0
             e = e.reshape(x.shape)
             try:
-                col = _np.imag(_np.asarray(fun(_as_array(x.astype(complex) + 1j * _H * e)))) / _H
+                import warnings as _warnings
+
+                with _warnings.catch_warnings():
+                    _warnings.simplefilter("ignore")
+                    res = _np.asarray(fun(_as_array(x.astype(complex) + 1j * _H * e)))
+                if not _np.iscomplexobj(res):
+                    raise TypeError("function is not complex-differentiable")
+                col = _np.imag(res) / _H
             except (TypeError, ValueError):
                 h = 1e-6
                 col = (_np.asarray(fun(_as_array(x + h * e))) - _np.asarray(fun(_as_array(x - h * e)))) / (2 * h)

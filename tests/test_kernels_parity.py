@@ -119,6 +119,25 @@ def test_algebra_hierarchy(be):
     np.testing.assert_allclose(k.diag(x), ko.diag(x), rtol=1e-13)
 
 
+def test_covariances_are_mutable_after_first_use(be):
+    """The reference's tests assign ``cov.active_dims`` (and users assign ``ls``) AFTER a first evaluation
+    (tests/test_base_cov.py:31-37): the compiled device program must follow the object's current state."""
+    rng = np.random.default_rng(6)
+    x, y = rng.random((30, 5)), rng.random((21, 5))
+    k, ko = C.Matern32(1.4) + C.Exponential(3.4), O.Matern32(1.4) + O.Exponential(3.4)
+    np.testing.assert_allclose(np.asarray(k(x, y)), ko(x, y), rtol=1e-13)
+    for ad in (slice(2), 1, slice(None, None, 2), [0, 3]):
+        k.active_dims = ad
+        ko.active_dims = ad
+        np.testing.assert_allclose(np.asarray(k(x, y)), ko(x, y), rtol=1e-13)
+    leaf, leafo = C.ExpQuad(0.9), O.ExpQuad(0.9)
+    np.testing.assert_allclose(np.asarray(leaf(x, y)), leafo(x, y), rtol=1e-13)
+    leaf.ls, leafo.ls = 2.5, 2.5
+    np.testing.assert_allclose(np.asarray(leaf(x, y)), leafo(x, y), rtol=1e-13)
+    back = C.Covariance.from_json(k.to_json())
+    np.testing.assert_allclose(np.asarray(back(x, y)), ko(x, y), rtol=1e-13)
+
+
 def test_empty_inputs(be):
     x = np.zeros((0, 3))
     y = np.random.default_rng(0).random((4, 3))
