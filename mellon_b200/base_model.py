@@ -18,6 +18,7 @@ from .inference import (
     DEFAULT_OPTIMIZER,
     compute_laplace_std,
     minimize_adam,
+    run_advi,
     minimize_lbfgsb,
 )
 from .parameter_validation import validate_cov_func, validate_cov_func_curry, validate_params
@@ -220,11 +221,11 @@ class BaseEstimator:
             self.opt_state = results.opt_state
             self.losses = results.losses
         elif optimizer == "advi":
-            raise NotImplementedError(
-                "optimizer='advi' is outside the accelerated path of mellon_b200 (SURVEY.md §2 row 5); "
-                "use 'L-BFGS-B' (default) or 'adam', with predictor_with_uncertainty=True for the "
-                "Laplace posterior."
-            )
+            results = run_advi(function, initial_value, n_iter=self.n_iter, init_learn_rate=self.init_learn_rate,
+                               jit=self.jit)
+            self.pre_transformation = results.pre_transformation
+            self.pre_transformation_std = results.pre_transformation_std
+            self.losses = results.losses
         elif optimizer == "L-BFGS-B":
             results = minimize_lbfgsb(function, initial_value, jit=self.jit)
             self.pre_transformation = results.pre_transformation

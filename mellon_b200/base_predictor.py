@@ -33,6 +33,40 @@ def _feature_error(expected, got):
     )
 
 
+
+def _central_gradient(f, x, cols, h_rel=1e-5):
+    """d f / d x[:, j] for j in ``cols`` by central differences; ``f`` maps (n, d) -> (n,).  Each column costs two
+    evaluations of the (device) predictor mean."""
+    x = np.asarray(x, dtype=float)
+    out = np.empty((x.shape[0], len(cols)))
+    for a, j in enumerate(cols):
+        h = h_rel * max(1.0, float(np.max(np.abs(x[:, j])))) if x.shape[0] else h_rel
+        e = np.zeros(x.shape[1])
+        e[j] = h
+        out[:, a] = (np.asarray(f(x + e)) - np.asarray(f(x - e))) / (2.0 * h)
+    return out
+
+
+def _central_hessian(f, x, cols, h_rel=1e-4):
+    """Second derivatives over the columns ``cols`` by central differences: (n, len(cols), len(cols))."""
+    x = np.asarray(x, dtype=float)
+    k = len(cols)
+    out = np.empty((x.shape[0], k, k))
+    hs = [h_rel * max(1.0, float(np.max(np.abs(x[:, j])))) if x.shape[0] else h_rel for j in cols]
+    f0 = np.asarray(f(x))
+    for a, j in enumerate(cols):
+        ej = np.zeros(x.shape[1])
+        ej[j] = hs[a]
+        out[:, a, a] = (np.asarray(f(x + ej)) - 2.0 * f0 + np.asarray(f(x - ej))) / hs[a] ** 2
+        for b in range(a + 1, k):
+            ek = np.zeros(x.shape[1])
+            ek[cols[b]] = hs[b]
+            v = (np.asarray(f(x + ej + ek)) - np.asarray(f(x + ej - ek)) - np.asarray(f(x - ej + ek))
+                 + np.asarray(f(x - ej - ek))) / (4.0 * hs[a] * hs[b])
+            out[:, a, b] = out[:, b, a] = v
+    return out
+
+
 class Predictor(ABC):
     """Callable posterior-mean predictor (``base_predictor.py:41-734``)."""
 
@@ -129,6 +163,21 @@ class Predictor(ABC):
     def uncertainty(self, x, diag=True):
         x = self._check_x(x)
         return self._covariance(x, diag=diag) + self._mean_covariance(x, diag=diag)
+
+    # -- derivatives of the mean (base_predictor.py:490-539).  The reference differentiates with JAX; here the
+    # device-evaluated mean is differenced centrally (relative error ~1e-9 for the gradient, ~1e-6 for the
+    # Hessian): an API-compatible host utility, not part of the accelerated path.
+    def gradient(self, x, jit=True):
+        x = ensure_2d(self._check_x(x))
+        return _central_gradient(self._mean, x, list(range(x.shape[1])))
+
+    def hessian(self, x, jit=True):
+        x = ensure_2d(self._check_x(x))
+        return _central_hessian(self._mean, x, list(range(x.shape[1])))
+
+    def hessian_log_determinant(self, x, jit=True):
+        sign, logdet = np.linalg.slogdet(self.hessian(x))
+        return sign, logdet
 
     def _data_dict(self):
         return {key: getattr(self, key) for key in self._state_variables}
@@ -268,3 +317,25 @@ class PredictorTime(Predictor):
     def uncertainty(self, Xnew, time=None, diag=True):
         Xnew = self._check_time_x(Xnew, time)
         return self._covariance(Xnew, diag=diag) + self._mean_covariance(Xnew, diag=diag)
+
+    # -- derivatives (base_predictor.py:1052-1194): with respect to the state columns at fixed time, and with
+    # respect to time; central differences of the device-evaluated mean, as in Predictor.gradient
+    @make_multi_time_argument
+    def time_derivative(self, x, time=None, jit=True):
+        Xnew = np.asarray(self._check_time_x(x, time), dtype=float)
+        return _central_gradient(self._mean, Xnew, [Xnew.shape[1] - 1])[:, 0]
+
+    @make_multi_time_argument
+    def gradient(self, x, time=None, jit=True):
+        Xnew = np.asarray(self._check_time_x(x, time), dtype=float)
+        return _central_gradient(self._mean, Xnew, list(range(Xnew.shape[1] - 1)))
+
+    @make_multi_time_argument
+    def hessian(self, x, time=None, jit=True):
+        Xnew = np.asarray(self._check_time_x(x, time), dtype=float)
+        return _central_hessian(self._mean, Xnew, list(range(Xnew.shape[1] - 1)))
+
+    @make_multi_time_argument
+    def hessian_log_determinant(self, x, time=None, jit=True):
+        sign, logdet = np.linalg.slogdet(self.hessian(x, time))
+        return sign, logdet

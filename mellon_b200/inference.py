@@ -44,11 +44,20 @@ class Transform:
 
     def __init__(self, mu, L):
         be = get_backend()
-        self.mu = float(mu)
+        # the estimators pass a scalar mean; the reference also accepts one value per cell (mu + L z broadcasts)
+        self.mu_vector = None
+        if np.ndim(mu) > 0 and np.size(mu) > 1:
+            self.mu_vector = np.asarray(mu, dtype=float).reshape(-1)
+            self.mu = 0.0
+        else:
+            self.mu = float(np.asarray(mu, dtype=float).reshape(-1)[0]) if np.ndim(mu) else float(mu)
         self.L = L if isinstance(L, DeviceArray) else be.upload(np.asarray(L, dtype=float), sharded=True)
+        if self.mu_vector is not None and self.mu_vector.shape[0] != self.L.shape[0]:
+            raise ValueError(f"mu has {self.mu_vector.shape[0]} entries, L has {self.L.shape[0]} rows.")
 
     def __call__(self, z):
-        return get_backend().transform(self.L, np.asarray(z, dtype=float), self.mu)
+        f = get_backend().transform(self.L, np.asarray(z, dtype=float), self.mu)
+        return f if self.mu_vector is None else f + self.mu_vector
 
 
 def compute_transform(mu, L):
@@ -85,7 +94,12 @@ class LossFunction:
             raise ValueError(f"nn_distances has shape {np.shape(nn_distances)}, but L has {n} rows.")
         self.k = int(k)
         self.transform = transform
-        self._state = get_backend().objective(transform.L, V, float(np.sum(Vdr)), transform.mu, self.k)
+        sum_vdr = float(np.sum(Vdr))
+        if transform.mu_vector is not None:
+            # per-cell mean: exp(L z + mu_i + V_i) and sum_i (L z + mu_i) — fold mu_i into V and into the constant
+            V = V + transform.mu_vector
+            sum_vdr += float(np.sum(transform.mu_vector))
+        self._state = get_backend().objective(transform.L, V, sum_vdr, transform.mu, self.k)
         self.n_evaluations = 0
 
     def value_and_grad(self, z):
@@ -173,6 +187,54 @@ def minimize_adam(loss_func, initial_value, n_iter=DEFAULT_N_ITER, init_learn_ra
         z = z - np.exp(-1e-2 * i) * init_learn_rate * mhat / (np.sqrt(vhat) + eps)
     Results = namedtuple("Results", "pre_transformation opt_state losses")
     return Results(z, (z, m, v), np.stack(losses))
+
+
+DEFAULT_NUM_SAMPLES = 40
+
+
+def run_advi(loss_func, initial_parameters, n_iter=DEFAULT_N_ITER, init_learn_rate=DEFAULT_INIT_LEARN_RATE,
+             nsamples=DEFAULT_NUM_SAMPLES, jit=DEFAULT_JIT):
+    """Mean-field Gaussian variational inference with Adam (inference.py:768-876).
+
+    The reference differentiates a Monte-Carlo ELBO with JAX; with the reparametrisation
+    ``z = mean + exp(log_std) eps`` its gradients are ``E[grad loss(z)]`` for the mean and
+    ``E[grad loss(z) eps std] - 1`` for ``log_std``, so every sample is one device pass of the same fused
+    loss + gradient kernel L-BFGS-B uses.  As in the reference the sampler is re-keyed with the iteration
+    number, the initial ``log_std`` is 0 and the step decays as ``exp(-0.01 t)``; the random streams are
+    NumPy's, not threefry's, so individual ELBO values differ from a JAX run (a stochastic optimiser)."""
+    fun = _value_and_grad(loss_func)
+    mean = np.array(initial_parameters, dtype=np.float64)
+    log_std = np.zeros_like(mean)
+    params = [mean, log_std]
+    m = [np.zeros_like(mean), np.zeros_like(mean)]
+    v = [np.zeros_like(mean), np.zeros_like(mean)]
+    b1, b2, eps_adam = 0.9, 0.999, 1e-8
+    half_log_2pi = 0.5 * np.log(2.0 * np.pi)
+    objective_values = []
+    for t in range(n_iter):
+        eps = np.random.default_rng(t).standard_normal((nsamples,) + mean.shape)
+        std = np.exp(params[1])
+        g_mean = np.zeros_like(mean)
+        g_log_std = np.zeros_like(mean)
+        total = 0.0
+        for s in range(nsamples):
+            value, g = fun(params[0] + std * eps[s])
+            g = np.asarray(g, dtype=np.float64)
+            log_q = float(np.sum(-0.5 * eps[s] ** 2 - params[1] - half_log_2pi))
+            total += float(value) + log_q          # -(logprob - log q) with logprob = -loss
+            g_mean += g
+            g_log_std += g * eps[s] * std
+        objective_values.append(total / nsamples)
+        grads = [g_mean / nsamples, g_log_std / nsamples - 1.0]
+        step = np.exp(-1e-2 * t) * init_learn_rate
+        for i in range(2):
+            m[i] = (1 - b1) * grads[i] + b1 * m[i]
+            v[i] = (1 - b2) * np.square(grads[i]) + b2 * v[i]
+            mhat = m[i] / (1 - b1 ** (t + 1))
+            vhat = v[i] / (1 - b2 ** (t + 1))
+            params[i] = params[i] - step * mhat / (np.sqrt(vhat) + eps_adam)
+    Results = namedtuple("Results", "pre_transformation pre_transformation_std losses")
+    return Results(params[0], np.exp(params[1]), objective_values)
 
 
 def compute_laplace_std(loss_func, pre_transformation, jit=DEFAULT_JIT):

@@ -224,6 +224,16 @@ def compute_d(x):
     return 1 if len(np.shape(x)) < 2 else np.shape(x)[1]
 
 
+def compute_d_factal(x, k=10, n=500, seed=432):
+    """Average local fractal dimension (parameters.py:545-583).  Outside this package's path (SURVEY.md §2:
+    `d_method="fractal"` draws its sample with jax.random and belongs to the dimensionality estimator's family);
+    the name exists so that code importing it from ``mellon.parameters`` loads, and says so when called."""
+    raise NotImplementedError(
+        "compute_d_factal (d_method='fractal') is outside mellon_b200's path; pass d= explicitly or use "
+        "d_method='embedding'."
+    )
+
+
 def compute_mu(nn_distances, d):
     """1st percentile of the NN maximum-likelihood log density, minus 10 (parameters.py:586-599)."""
     return float(np.quantile(mle(nn_distances, d), 0.01)) - 10

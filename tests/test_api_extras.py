@@ -1,0 +1,95 @@
+"""API-surface pieces next to the accelerated path, exercised on both backends (the NumPy test double on CPU, the
+CUDA library on a GPU): ADVI on the device loss + gradient, numerical predictor derivatives, per-cell mean in the
+functional transform / loss API.  The reference's own test files for these run against the package through
+tools/run_reference_tests.py; the checks here are the parts that can be pinned numerically."""
+
+import numpy as np
+import pytest
+
+import mellon_b200 as mb
+from oracle import mellon_oracle as O
+
+
+def _cells(n=300, d=3, seed=0):
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal((n, d)) * 0.7
+
+
+def test_advi_runs_on_the_device_objective_and_agrees_with_map(be):
+    X = _cells()
+    nn = O.compute_nn_distances(X)
+    lm = X[:40].copy()
+    est_map = mb.DensityEstimator(landmarks=lm, nn_distances=nn, predictor_with_uncertainty=True)
+    dens_map = est_map.fit_predict(X)
+    est = mb.DensityEstimator(landmarks=lm, nn_distances=nn, optimizer="advi", n_iter=60, predictor_with_uncertainty=True)
+    dens = est.fit_predict(X)
+    assert dens.shape == (300,) and len(est.losses) == 60
+    assert est.pre_transformation_std is not None and np.all(est.pre_transformation_std > 0)
+    assert np.corrcoef(dens, dens_map)[0, 1] > 0.8          # tests/test_laplace.py:170-208 asks for > 0.8
+    unc = est.predict.uncertainty(X[:20])
+    assert unc.shape == (20,) and np.all(unc > 0)
+    # deterministic: the sampler is re-keyed with the iteration number
+    again = mb.DensityEstimator(landmarks=lm, nn_distances=nn, optimizer="advi", n_iter=60).fit_predict(X)
+    np.testing.assert_array_equal(again, dens)
+
+
+def test_run_advi_on_a_plain_callable(be):
+    res = mb.inference.run_advi(lambda x: float(np.sum(np.asarray(x) ** 2)), np.ones(2), n_iter=50, nsamples=10)
+    assert res.pre_transformation.shape == (2,) and res.pre_transformation_std.shape == (2,) and len(res.losses) == 50
+    assert np.max(np.abs(res.pre_transformation)) < 1.0
+
+
+def test_predictor_derivatives_match_finite_differences_of_the_oracle(be):
+    X = _cells(200, 2, 1)
+    nn = O.compute_nn_distances(X)
+    lm = X[:30].copy()
+    est = mb.DensityEstimator(landmarks=lm, nn_distances=nn)
+    est.fit(X)
+    Y = _cells(15, 2, 2)
+    g = est.predict.gradient(Y)
+    H = est.predict.hessian(Y)
+    sign, logdet = est.predict.hessian_log_determinant(Y)
+    assert g.shape == Y.shape and H.shape == (15, 2, 2) and sign.shape == (15,) and logdet.shape == (15,)
+    np.testing.assert_allclose(H, np.swapaxes(H, 1, 2), atol=1e-12)
+    # independent check: analytic gradient of mu + k(y, xu) w through the covariance's own k_grad
+    w = np.asarray(est.predict.weights) if hasattr(est.predict, "weights") else None
+    if w is not None:
+        kg = np.asarray(est.cov_func.k_grad(np.asarray(est.landmarks))(Y))     # (m, n, d)
+        np.testing.assert_allclose(g, np.einsum("i,ijd->jd", w.reshape(-1), kg), rtol=1e-6, atol=1e-8)
+
+
+def test_time_predictor_derivatives_shapes(be):
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((160, 2)) * 0.5
+    times = np.repeat(np.arange(4.0), 40)
+    est = mb.TimeSensitiveDensityEstimator(ls=1.0, ls_time=1.0, landmarks=np.concatenate([X[::8], times[::8, None]], axis=1))
+    est.fit(X, times)
+    g = est.predict.gradient(X[:10], 1.0)
+    H = est.predict.hessian(X[:10], 1.0)
+    td = est.predict.time_derivative(X[:10], 1.0)
+    assert g.shape == (10, 2) and H.shape == (10, 2, 2) and td.shape == (10,)
+    gm = est.predict.gradient(X[:10], multi_time=[0.0, 1.0, 2.0])
+    assert gm.shape == (10, 3, 2)
+    h = 1e-5
+    np.testing.assert_allclose(td, (est.predict(X[:10], 1.0 + h) - est.predict(X[:10], 1.0 - h)) / (2 * h), rtol=1e-5, atol=1e-7)
+
+
+def test_per_cell_mean_in_transform_and_loss(be):
+    rng = np.random.default_rng(4)
+    n, r = 150, 9
+    L = rng.standard_normal((n, r)) / 3
+    nn = rng.random(n) * 0.3 + 0.05
+    mu = rng.standard_normal(n) * 0.1 - 3.0
+    z = rng.standard_normal(r) * 0.2
+    tr = mb.inference.compute_transform(mu, L)
+    lf = mb.inference.compute_loss_func(nn, 5.0, tr, r)
+    loss, grad = lf.value_and_grad(z)
+    f = L @ z + mu
+    V, Vdr = O.nn_constants(nn, 5.0)
+    A = np.exp(f + V)
+    ref = 0.5 * z @ z + 0.5 * r * np.log(2 * np.pi) - np.sum(f + Vdr - A)
+    np.testing.assert_allclose(tr(z), f, rtol=1e-13)
+    assert abs(loss - ref) <= 1e-12 * abs(ref)
+    np.testing.assert_allclose(grad, z + L.T @ (A - 1.0), rtol=1e-11, atol=1e-12)
+    with pytest.raises(ValueError):
+        mb.inference.compute_transform(mu[:-1], L)
