@@ -23,6 +23,14 @@ from . import _native as nat
 from .util import deserialize, expand_to_inactive, make_serializable, select_active_dims
 
 MELLON_NAME = __name__.split(".")[0]
+
+
+def wire_module_name(module_name):
+    """Module path written into serialised documents.  This package's classes are written under the reference's
+    module path (``mellon.cov``, ``mellon.conditional`` — same class names there), so a file written here loads
+    in stock Mellon; the loaders below resolve those names to the classes of this package."""
+    head, _, rest = module_name.partition(".")
+    return "mellon" + ("." + rest if rest else "") if head == MELLON_NAME else module_name
 logger = logging.getLogger("mellon")
 
 
@@ -177,7 +185,7 @@ class Covariance(ABC):
     def _data_dict(self):
         return {key: make_serializable(val) for key, val in self.__dict__.items()}
 
-    def _metadata(self):
+    def _metadata(self, package_only=False):
         module_name = self.__class__.__module__
         clsname = self.__class__.__name__
         if module_name == "__main__" or module_name.split(".")[0] != MELLON_NAME:
@@ -188,7 +196,8 @@ class Covariance(ABC):
         meta = import_module(module_name.split(".")[0]) if module_name != "__main__" else None
         return {
             "classname": clsname,
-            "module_name": module_name,
+            # pairs record the package alone, leaves the full module path (base_cov.py:254 against :124)
+            "module_name": wire_module_name(module_name.split(".")[0] if package_only else module_name),
             "module_version": getattr(meta, "__version__", "NA"),
             "serialization_date": datetime.now().isoformat(),
             "python_version": sys.version,
@@ -256,7 +265,7 @@ class CovariancePair(Covariance):
             "left_data": self.left.__getstate__(),
             "right_data": right,
             "active_dims": make_serializable(self.active_dims),
-            "metadata": self._metadata(),
+            "metadata": self._metadata(package_only=True),
         }
 
     def __setstate__(self, state):

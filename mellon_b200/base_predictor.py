@@ -18,7 +18,7 @@ from typing import List, Set, Union
 import numpy as np
 from packaging import version
 
-from .base_cov import Covariance
+from .base_cov import Covariance, wire_module_name
 from .util import deserialize, ensure_2d, make_multi_time_argument, make_serializable, object_html, object_str
 from .validation import validate_array, validate_bool, validate_time_x
 
@@ -201,7 +201,7 @@ class Predictor(ABC):
             "cov_func": self.cov_func.__getstate__(),
             "metadata": {
                 "classname": self.__class__.__name__,
-                "module_name": module_name,
+                "module_name": wire_module_name(module_name),
                 "module_version": getattr(meta, "__version__", "NA"),
                 "serialization_date": datetime.now().isoformat(),
                 "python_version": sys.version,

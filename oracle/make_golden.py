@@ -152,6 +152,51 @@ def main():
                       fit_args=(times,), pred_args=(times[:30],))
     save("time_sensitive", X=Xt, times=times, Y=Xt[:30], Y_times=times[:30], **out)
 
+    serialised_predictors()
+
+
+def serialised_predictors():
+    """Predictors fitted AND serialised by the reference (``Predictor.to_json``, base_predictor.py:541-734), with the
+    reference's own predictions at a few query points: tests/test_serialisation_interop.py loads the JSON text with
+    this package and must reproduce them."""
+    import json
+
+    C = mellon.cov
+    cases = {}
+    Xc, Yc = blobs(300, 4, 41), blobs(12, 4, 42)
+    lmc = Xc[:30].copy()
+    X1 = np.random.default_rng(5).random((60, 3))
+    Xt = np.concatenate([blobs(50, 2, 50 + t) + 0.2 * t for t in range(3)])
+    times = np.repeat(np.arange(3.0), 50)
+    lmt = np.concatenate([Xt, times[:, None]], axis=1)[::6].copy()
+    todo = {
+        "sparse_cholesky_laplace": (lambda: mellon.DensityEstimator(landmarks=lmc, predictor_with_uncertainty=True), Xc, (), Yc, ()),
+        "sparse_nystroem": (lambda: mellon.DensityEstimator(landmarks=lmc, rank=12), Xc, (), Yc, ()),
+        "full": (lambda: mellon.DensityEstimator(cov_func_curry=C.ExpQuad), X1, (), X1[:9] + 0.01, ()),
+        "time_sensitive": (lambda: mellon.TimeSensitiveDensityEstimator(ls=1.5, ls_time=0.8, landmarks=lmt), Xt, (times,), Xt[:10], (times[:10],)),
+    }
+    for name, (make, X, fit_args, Y, pred_args) in todo.items():
+        est = make()
+        est.fit(X, *fit_args)
+        pred = est.predict
+        case = {"json": pred.to_json(), "Y": A(Y).tolist(), "pred_args": [A(a).tolist() for a in pred_args],
+                "mean": A(pred(Y, *pred_args)).tolist(), "mean_normalized": A(pred(Y, *pred_args, normalize=True)).tolist(),
+                "classname": type(pred).__name__, "cov_func_json": est.cov_func.to_json()}
+        if name == "sparse_cholesky_laplace":
+            case["covariance"] = A(pred.covariance(Y)).tolist()
+            case["mean_covariance"] = A(pred.mean_covariance(Y)).tolist()
+            case["uncertainty"] = A(pred.uncertainty(Y)).tolist()
+        if name == "time_sensitive":
+            case["mean_multi_time"] = A(pred(Y[:, :], multi_time=[0.0, 1.5])).tolist()
+        cases[name] = case
+    path = os.path.join(OUT, "reference_predictors.json")
+    with open(path, "w") as f:
+        json.dump(cases, f)
+    print(f"{path}: {os.path.getsize(path) / 1024:.1f} KiB, cases={sorted(cases)}")
+
 
 if __name__ == "__main__":
-    main()
+    if "--predictors-only" in sys.argv:
+        serialised_predictors()
+    else:
+        main()
