@@ -136,8 +136,14 @@ int mb_mat_fill(mb_ctx* ctx, mb_mat* m, double v);
 int mb_mat_transpose(mb_ctx* ctx, const mb_mat* src, mb_mat* dst);
 /* A += v * I                      util.py:269-293 (stabilize / add_diagonal) */
 int mb_mat_add_diag(mb_ctx* ctx, mb_mat* a, double v);
+/* A(i, i) += v(i)                 conditional.py:245,320,347 (`K + sigma_g**2 * eye(n)` with one noise level per
+ * observation: the (n, p) sigma form of FunctionEstimator) */
+int mb_mat_add_diag_vec(mb_ctx* ctx, mb_mat* a, const mb_mat* v);
 /* a(i, j) *= s(j)                 decomposition.py:265 (`* sqrt(S)`), inference.py:372 */
 int mb_mat_scale_cols(mb_ctx* ctx, mb_mat* a, const mb_mat* s);
+/* A(i, :) *= s(i)  (local rows)   conditional.py:531-533 (`A / sigma2` with one sigma per observation, on the
+ * transposed layout this library keeps) */
+int mb_mat_scale_rows(mb_ctx* ctx, mb_mat* a, const mb_mat* s);
 /* dst <- src[:, c0:c0+ncols]      decomposition.py:75-76 (`v[:, -p:]`) */
 int mb_mat_copy_cols(mb_ctx* ctx, const mb_mat* src, int64_t c0, int64_t ncols, mb_mat* dst);
 /* copy the lower triangle onto the upper one (symmetrise a lower-only result) */

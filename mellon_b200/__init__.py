@@ -1,7 +1,7 @@
 """mellon_b200 — B200-native drop-in for the sparse-GP density path of settylab/Mellon.
 
 ``import mellon_b200 as mellon`` gives the surface of ``mellon/__init__.py`` for that path:
-``DensityEstimator``, ``TimeSensitiveDensityEstimator``, ``Predictor``, ``Covariance`` and the
+``DensityEstimator``, ``TimeSensitiveDensityEstimator``, ``FunctionEstimator``, ``Predictor``, ``Covariance`` and the
 sub-modules ``cov``, ``util``, ``parameters``, ``inference``, ``conditional``,
 ``decomposition``, ``validation``.  Importing the package needs neither a GPU nor the shared
 library; the first numeric call does, and fails loudly without them (no CPU fallback).
@@ -47,10 +47,11 @@ from . import conditional, cov, decomposition, inference, parameters, util, vali
 from .backend import get_backend, set_backend  # noqa: E402
 from .base_cov import Covariance  # noqa: E402
 from .base_predictor import Predictor  # noqa: E402
-from .model import DensityEstimator, TimeSensitiveDensityEstimator  # noqa: E402
+from .model import DensityEstimator, FunctionEstimator, TimeSensitiveDensityEstimator  # noqa: E402
 
 __all__ = [
     "DensityEstimator",
+    "FunctionEstimator",
     "TimeSensitiveDensityEstimator",
     "Predictor",
     "Covariance",

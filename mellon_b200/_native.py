@@ -92,7 +92,9 @@ SIGNATURES = {
     "mb_mat_fill": (_i, [_vp, _vp, _d]),
     "mb_mat_transpose": (_i, [_vp, _vp, _vp]),
     "mb_mat_add_diag": (_i, [_vp, _vp, _d]),
+    "mb_mat_add_diag_vec": (_i, [_vp, _vp, _vp]),
     "mb_mat_scale_cols": (_i, [_vp, _vp, _vp]),
+    "mb_mat_scale_rows": (_i, [_vp, _vp, _vp]),
     "mb_mat_copy_cols": (_i, [_vp, _vp, _i64, _i64, _vp]),
     "mb_mat_symmetrize": (_i, [_vp, _vp]),
     "mb_mat_scale": (_i, [_vp, _vp, _d]),

@@ -384,6 +384,12 @@ class CudaBackend:
         nat.check(self.lib.mb_mat_add_diag(self.ctx, A._h, float(value)), "mb_mat_add_diag")
         return A
 
+    def add_diag_vec(self, A, v):
+        """A(i, i) += v(i) for a replicated square matrix."""
+        vd = self.upload(np.asarray(v, dtype=np.float64))
+        nat.check(self.lib.mb_mat_add_diag_vec(self.ctx, A._h, vd._h), "mb_mat_add_diag_vec")
+        return A
+
     def potrf(self, A):
         return nat.check(self.lib.mb_potrf(self.ctx, A._h), "mb_potrf")
 
@@ -476,6 +482,12 @@ class CudaBackend:
     def scale_cols(self, A, s):
         sd = self.upload(np.asarray(s, dtype=np.float64))
         nat.check(self.lib.mb_mat_scale_cols(self.ctx, A._h, sd._h), "mb_mat_scale_cols")
+        return A
+
+    def scale_rows(self, A, s):
+        """A(i, :) *= s(i); ``s`` is the full (global) vector, cut like the rows of a sharded A."""
+        sd = self.upload(np.asarray(s, dtype=np.float64), sharded=A.sharded)
+        nat.check(self.lib.mb_mat_scale_rows(self.ctx, A._h, sd._h), "mb_mat_scale_rows")
         return A
 
     def copy_cols(self, A, c0, ncols):

@@ -146,6 +146,35 @@ class Predictor(ABC):
 
     __call__ = mean
 
+    # -- regression diagnostics (FunctionEstimator; base_predictor.py:259-355) -----------------------------
+    def _leverage(self, Xnew, sigma):
+        raise NotImplementedError(f"{self.__class__.__name__} does not define a leverage.")
+
+    def leverage(self, x):
+        """Diagonal of the GP hat matrix ``H = K (K + sigma^2 I)^-1`` (``base_predictor.py:263-288``):
+        shape ``(n,)``, or ``(n, p)`` with a per-feature sigma."""
+        return self._leverage(self._check_x(x), self.sigma)
+
+    def loo_residuals_squared(self, x, y):
+        """Squared leave-one-out residuals through the HC3 shortcut ``r_i^2 / (1 - h_i)^2``
+        (``base_predictor.py:290-325``)."""
+        x = validate_array(x, "x")
+        y = validate_array(y, "y")
+        x = self._check_x(x)
+        residual = y - self._mean(x)
+        h = self._leverage(x, self.sigma)
+        if residual.ndim > h.ndim:
+            h = h[..., None]
+        return residual ** 2 / (1 - h) ** 2
+
+    def _obs_variance(self, Xnew):
+        raise NotImplementedError(f"{self.__class__.__name__} does not define an observation variance.")
+
+    def obs_variance(self, x):
+        """GP-smoothed corrected squared residuals: an input-dependent estimate of the observation noise
+        variance (``base_predictor.py:330-355``)."""
+        return self._obs_variance(self._check_x(x))
+
     @abstractmethod
     def _covariance(self, *args, **kwargs):
         """Posterior covariance of the GP at validated inputs."""
@@ -154,7 +183,20 @@ class Predictor(ABC):
     def _mean_covariance(self, *args, **kwargs):
         """Covariance of the mean induced by parameter uncertainty."""
 
+    def _has_per_feature_sigma(self):
+        return getattr(self, "per_feature_sigma", False)
+
     def covariance(self, x, diag=True, noise_free=False):
+        """Posterior (co)variance (``base_predictor.py:361-418``).  A predictor fitted with a per-feature sigma
+        only has the noise-free covariance, which the caller must acknowledge with ``noise_free=True``."""
+        if self._has_per_feature_sigma() and not noise_free:
+            raise ValueError(
+                "This predictor was fitted with per-feature sigma, so the "
+                "covariance is noise-free (sigma=0) and does not include "
+                "observation noise. Pass noise_free=True to acknowledge this "
+                "and obtain the noise-free covariance, then account for "
+                "observation noise separately (e.g., via obs_variance)."
+            )
         return self._covariance(self._check_x(x), diag=diag)
 
     def mean_covariance(self, x, diag=True):

@@ -244,6 +244,17 @@ __global__ void k_add_diag(double* a, int64_t n, int64_t ld, double v) {
   if (i < n) a[i * ld + i] += v;
 }
 
+__global__ void k_add_diag_vec(double* a, int64_t n, int64_t ld, const double* __restrict__ v) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) a[i * ld + i] += v[i];
+}
+
+__global__ void k_scale_rows(double* a, int64_t rows, int64_t cols, const double* __restrict__ s) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+  int64_t n = rows * cols;
+  for (; i < n; i += st) a[i] *= s[i / cols];
+}
+
 __global__ void k_transpose(const double* __restrict__ src, double* __restrict__ dst, int64_t rows,
                             int64_t cols) {
   __shared__ double tile[32][33];
@@ -471,6 +482,30 @@ extern "C" int mb_mat_add_diag(mb_ctx* c, mb_mat* a, double v) {
   MB_CUDA(cudaSetDevice(c->device));
   if (a->rows == 0) return 0;
   MB_LAUNCH(c, k_add_diag, (int)ceil_div64(a->rows, 256), 256, 0, a->p, a->rows, a->cols, v);
+  return 0;
+}
+
+extern "C" int mb_mat_add_diag_vec(mb_ctx* c, mb_mat* a, const mb_mat* v) {
+  MB_CHECK(c && a && v, "mb_mat_add_diag_vec: null argument");
+  MB_CHECK(a->rows == a->cols, "mb_mat_add_diag_vec: matrix is %lld x %lld, not square",
+           (long long)a->rows, (long long)a->cols);
+  MB_CHECK(v->rows * v->cols == a->rows, "mb_mat_add_diag_vec: %lld diagonal entries for %lld rows",
+           (long long)(v->rows * v->cols), (long long)a->rows);
+  MB_CUDA(cudaSetDevice(c->device));
+  if (a->rows == 0) return 0;
+  MB_LAUNCH(c, k_add_diag_vec, (int)ceil_div64(a->rows, 256), 256, 0, a->p, a->rows, a->cols, v->p);
+  return 0;
+}
+
+extern "C" int mb_mat_scale_rows(mb_ctx* c, mb_mat* a, const mb_mat* s) {
+  MB_CHECK(c && a && s, "mb_mat_scale_rows: null argument");
+  MB_CHECK(s->rows * s->cols == a->rows, "mb_mat_scale_rows: scale has %lld entries for %lld rows",
+           (long long)(s->rows * s->cols), (long long)a->rows);
+  MB_CUDA(cudaSetDevice(c->device));
+  int64_t n = a->rows * a->cols;
+  if (n == 0) return 0;
+  int grid = (int)min((int64_t)c->n_sm * 8, ceil_div64(n, 256));
+  MB_LAUNCH(c, k_scale_rows, grid, 256, 0, a->p, a->rows, a->cols, s->p);
   return 0;
 }
 

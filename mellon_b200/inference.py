@@ -321,11 +321,10 @@ def compute_conditional(x, landmarks, pre_transformation, pre_transformation_std
 
     Chooses FullConditional (no landmarks), LandmarksConditionalCholesky (z has one entry per
     landmark) or LandmarksConditional (Nystroem ranks)."""
-    if obs_variance:
-        raise NotImplementedError("obs_variance belongs to FunctionEstimator, outside this package's path.")
+    extra = {"obs_variance": True} if obs_variance else {}
     return _build((FullConditional, LandmarksConditional, LandmarksConditionalCholesky), x, landmarks,
                   pre_transformation, pre_transformation_std, y, mu, cov_func, L, Lp, sigma, jitter, y_is_mean,
-                  with_uncertainty, time_variant=False)
+                  with_uncertainty, time_variant=False, **extra)
 
 
 def compute_conditional_times(x, landmarks, pre_transformation, pre_transformation_std, y, mu, cov_func, L, Lp,

@@ -153,6 +153,7 @@ def main():
     save("time_sensitive", X=Xt, times=times, Y=Xt[:30], Y_times=times[:30], **out)
 
     serialised_predictors()
+    function_estimator()
 
 
 def serialised_predictors():
@@ -195,8 +196,72 @@ def serialised_predictors():
     print(f"{path}: {os.path.getsize(path) / 1024:.1f} KiB, cases={sorted(cases)}")
 
 
+def function_estimator():
+    """FunctionEstimator (function_estimator.py:29-615) run by the reference: the two cases of the
+    reference's own golden test (tests/test_reference_results.py — inputs from ``jax.random.PRNGKey(42)`` through the
+    threefry restatement; the hard-coded tables of that file are asserted in tests/test_function_estimator.py), plus
+    a vector ``y``, ``y_is_mean``, per-feature sigma, predictive covariance and a clustered 400-cell problem."""
+    import jax
+
+    out = {}
+
+    def run(tag, X, y, Xq, landmarks=None, n_landmarks=None, no_leverage=False, **kw):
+        est = mellon.FunctionEstimator(landmarks=landmarks, n_landmarks=n_landmarks, **kw)
+        est.fit(X, y)
+        pred = est.predict
+        out[tag + "_X"], out[tag + "_y"], out[tag + "_Xq"] = A(X), A(y), A(Xq)
+        out[tag + "_ls"] = A(est.ls)
+        out[tag + "_predictor"] = np.array(type(pred).__name__)
+        if est.landmarks is not None:
+            out[tag + "_landmarks"] = A(est.landmarks)
+        out[tag + "_pred"] = A(pred(Xq))
+        out[tag + "_weights"] = A(pred.weights)
+        if not kw.get("y_is_mean", False) and not no_leverage:
+            out[tag + "_lev"] = A(pred.leverage(X))
+            out[tag + "_lev_q"] = A(pred.leverage(Xq))
+            out[tag + "_loo"] = A(pred.loo_residuals_squared(X, y))
+        if kw.get("obs_variance", False):
+            out[tag + "_obsvar"] = A(pred.obs_variance(Xq))
+            out[tag + "_variance_weights"] = A(pred.variance_weights)
+            out[tag + "_corrected_r2"] = A(est.loo_residuals_squared())
+        if kw.get("predictor_with_uncertainty", False):
+            nf = dict(noise_free=True) if pred.per_feature_sigma else {}
+            out[tag + "_covariance"] = A(pred.covariance(Xq, **nf))
+            out[tag + "_covariance_full"] = A(pred.covariance(Xq, diag=False, **nf))
+        return est
+
+    k1, k2, k3 = jax.random.split(jax.random.PRNGKey(42), 3)
+    X, y, Xq = A(jax.random.normal(k1, (50, 2))), A(jax.random.normal(k2, (50, 3))), A(jax.random.normal(k3, (10, 2)))
+    run("ref_full", X, y, Xq, n_landmarks=0, sigma=1.0, obs_variance=True)
+    sp = run("ref_sparse", X, y, Xq, n_landmarks=15, sigma=1.0, obs_variance=True)
+    lm = A(sp.landmarks)
+    run("full_unc", X, y, Xq, n_landmarks=0, sigma=0.7, predictor_with_uncertainty=True)
+    run("sparse_unc", X, y, Xq, landmarks=lm, sigma=0.7, predictor_with_uncertainty=True)
+    run("full_vec", X, y[:, 0], Xq, n_landmarks=0, sigma=0.5, obs_variance=True, mu=0.2)
+    run("sparse_vec", X, y[:, 0], Xq, landmarks=lm, sigma=0.5, obs_variance=True, mu=0.2)
+    run("full_mean", X, y, Xq, n_landmarks=0, y_is_mean=True)
+    run("sparse_mean", X, y[:, 1], Xq, landmarks=lm, y_is_mean=True)
+    pf = np.array([0.5, 1.0, 2.0])
+    run("full_pf", X, y, Xq, n_landmarks=0, sigma=pf, obs_variance=True, predictor_with_uncertainty=True)
+    run("sparse_pf", X, y, Xq, landmarks=lm, sigma=pf, obs_variance=True, predictor_with_uncertainty=True)
+    # one noise level per observation and output, and per observation for a vector y (tests/test_perobservation_sigma.py)
+    snp = 0.3 + np.random.default_rng(64).random((50, 3))
+    run("full_np", X, y, Xq, n_landmarks=0, sigma=snp, predictor_with_uncertainty=True, no_leverage=True)
+    run("sparse_np", X, y, Xq, landmarks=lm, sigma=snp, predictor_with_uncertainty=True, no_leverage=True)
+    run("full_obs", X, y[:, 2], Xq, n_landmarks=0, sigma=snp[:, 0], predictor_with_uncertainty=True, no_leverage=True)
+    run("sparse_obs", X, y[:, 2], Xq, landmarks=lm, sigma=snp[:, 0], predictor_with_uncertainty=True, no_leverage=True)
+    Xc, Xcq = blobs(400, 4, 61), blobs(30, 4, 62)
+    yc = np.stack([np.sin(Xc[:, 0]) + 0.1 * np.random.default_rng(63).standard_normal(400), Xc[:, 1] * Xc[:, 2]], axis=1)
+    run("clustered_sparse", Xc, yc, Xcq, landmarks=Xc[:40].copy(), sigma=0.3, obs_variance=True, ls=1.5,
+        cov_func_curry=mellon.cov.Matern32)
+    run("clustered_full", Xc[:150], yc[:150], Xcq, n_landmarks=0, sigma=0.3, obs_variance=True, ls=1.5)
+    save("function_estimator", **out)
+
+
 if __name__ == "__main__":
     if "--predictors-only" in sys.argv:
         serialised_predictors()
+    elif "--function-only" in sys.argv:
+        function_estimator()
     else:
         main()

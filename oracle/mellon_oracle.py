@@ -659,6 +659,193 @@ def conditional_mean(Xnew, base, weights, mu, cov_func):
 
 
 # --------------------------------------------------------------------------------------
+# function_estimator.py / conditional.py: regression on observed values y
+# --------------------------------------------------------------------------------------
+def is_per_feature_sigma(sigma, y):
+    """conditional.py:13-36"""
+    if sigma is None or np.ndim(sigma) == 0:
+        return False
+    sigma = np.asarray(sigma)
+    if sigma.ndim == 2 and sigma.shape[0] == 1 and np.ndim(y) == 2 and sigma.shape[1] == y.shape[1]:
+        return True
+    if sigma.ndim == 2 and np.ndim(y) == 2 and sigma.shape == y.shape:
+        return True
+    return sigma.ndim == 1 and np.ndim(y) == 2 and sigma.shape[0] == y.shape[1]
+
+
+def _sigma_columns(sigma, p):
+    """One noise level (scalar, or an n-vector for the (n, p) form) per output column:
+    ``_normalize_per_feature_sigma`` + the vmap axes of conditional.py:39-43, 249-252."""
+    sigma = np.asarray(sigma, dtype=float)
+    if sigma.ndim == 2 and sigma.shape[0] == 1 and sigma.shape[1] == p:
+        sigma = sigma[0]
+    return [sigma[:, g] if sigma.ndim == 2 else sigma[g] for g in range(p)]
+
+
+def _noise_chol(K, sigma_g, jitter):
+    """cholesky(stabilize(K + sigma_g**2 * eye(n), jitter))  (conditional.py:245, 320, 347)"""
+    n = K.shape[0]
+    return np.linalg.cholesky(stabilize(K + np.asarray(sigma_g) ** 2 * np.eye(n), jitter))
+
+
+def _chol_solve(L, b):
+    return solve_triangular(L.T, solve_triangular(L, b, lower=True))
+
+
+def _full_leverage(K, sigma_g, jitter):
+    """h = 1 - sigma^2 diag((K + sigma^2 I)^-1)  (conditional.py:319-330, 391-400)"""
+    Linv = solve_triangular(_noise_chol(K, sigma_g, jitter), np.eye(K.shape[0]), lower=True)
+    return 1 - np.asarray(sigma_g) ** 2 * np.sum(np.square(Linv), axis=0)
+
+
+FunctionFit = namedtuple("FunctionFit", "kind base weights mu cov_func sigma jitter per_feature L Cs "
+                                        "variance_weights corrected_r2")
+
+
+def function_full_conditional(x, y, mu, cov_func, sigma=0.0, jitter=DEFAULT_JITTER, y_is_mean=False,
+                              with_uncertainty=False, obs_variance=False):
+    """``_FullConditional.__init__`` + ``_compute_obs_variance`` as FunctionEstimator reaches them
+    (conditional.py:233-364; L is never passed on that route, function_estimator.py:356-371)."""
+    x = ensure_2d(x)
+    y = np.asarray(y, dtype=float)
+    K = cov_func(x, x)
+    per_feature = is_per_feature_sigma(sigma, y)
+    r = y - mu
+    if per_feature:
+        cols = _sigma_columns(sigma, y.shape[1])
+        weights = np.stack([_chol_solve(_noise_chol(K, s, jitter), r[:, g]) for g, s in enumerate(cols)], axis=1)
+        L = None
+    else:
+        # y_is_mean: chol(K + jitter I); else K + max(sigma^2, jitter) I  (add_variance with eye(n) * sigma)
+        L = np.linalg.cholesky(add_variance(K, None if y_is_mean else np.eye(x.shape[0]) * sigma, jitter))
+        weights = _chol_solve(L, r)
+    vw = cr2 = None
+    if obs_variance:
+        prediction = mu + K @ weights
+        if np.ndim(sigma) >= 1:
+            cols = _sigma_columns(sigma, y.shape[1])
+            h = np.stack([_full_leverage(K, s, jitter) for s in cols], axis=1)
+        else:
+            h = _full_leverage(K, sigma, jitter)
+        residual = y - prediction
+        if residual.ndim > h.ndim:
+            h = h[..., None]
+        cr2 = residual ** 2 / (1 - h) ** 2
+        if np.ndim(sigma) >= 1:
+            vw = np.stack([_chol_solve(_noise_chol(K, s, jitter), cr2[:, g]) for g, s in enumerate(cols)], axis=1)
+        else:
+            vw = _chol_solve(_noise_chol(K, sigma, jitter), cr2)
+    Lc = None
+    if with_uncertainty:
+        Lc = np.linalg.cholesky(stabilize(K, jitter)) if per_feature else L
+    return FunctionFit("full", x, weights, mu, cov_func, sigma, jitter, per_feature, Lc, None, vw, cr2)
+
+
+def _landmark_leverage(B, K_uu, sigma_g, jitter):
+    """diag(B (sigma^2 K_uu + B^T B + jitter I)^-1 B^T)  (conditional.py:602-616, 674-685)"""
+    M = stabilize(np.asarray(sigma_g) ** 2 * K_uu + B.T @ B, jitter)
+    return np.sum((B @ np.linalg.inv(M)) * B, axis=1)
+
+
+def function_landmarks_conditional(x, xu, y, mu, cov_func, sigma=0.0, jitter=DEFAULT_JITTER, y_is_mean=False,
+                                   with_uncertainty=False, obs_variance=False):
+    """``_LandmarksConditional.__init__`` + ``_compute_obs_variance`` (conditional.py:513-649)."""
+    x, xu = ensure_2d(x), ensure_2d(xu)
+    y = np.asarray(y, dtype=float)
+    Kuf = cov_func(xu, x)
+    per_feature = is_per_feature_sigma(sigma, y)
+    Lp = _get_L(xu, cov_func, jitter)
+    A = solve_triangular(Lp, Kuf, lower=True)
+    r = y - mu
+    L_B = None
+    if per_feature:
+        cols = _sigma_columns(sigma, y.shape[1])          # floats, or one n-vector per output for the (n, p) form
+        weights = np.stack([sparse_solve(Lp, A, r[:, g] / s ** 2, A / s ** 2)[0] for g, s in enumerate(cols)], axis=1)
+    elif y_is_mean:
+        weights, L_B = sparse_solve(Lp, A, r, A)
+    else:
+        s2 = np.asarray(sigma, dtype=float) ** 2          # `_process_sigma`, element-wise branch (conditional.py:155-159)
+        weights, L_B = sparse_solve(Lp, A, r / s2, A / s2)
+    vw = cr2 = None
+    if obs_variance:
+        B = Kuf.T
+        K_uu = Lp @ Lp.T
+        prediction = mu + B @ weights
+        if np.ndim(sigma) >= 1:
+            h = np.stack([_landmark_leverage(B, K_uu, s, jitter) for s in cols], axis=1)
+        else:
+            h = _landmark_leverage(B, K_uu, sigma, jitter)
+        residual = y - prediction
+        if residual.ndim > h.ndim:
+            h = h[..., None]
+        cr2 = residual ** 2 / (1 - h) ** 2
+        if np.ndim(sigma) >= 1:
+            vw = np.stack([sparse_solve(Lp, A, cr2[:, g] / s ** 2, A / s ** 2)[0] for g, s in enumerate(cols)], axis=1)
+        else:
+            s2 = float(sigma) ** 2
+            vw, _ = sparse_solve(Lp, A, cr2 / s2, A / s2)
+    Cs = Lp @ L_B if (with_uncertainty and not per_feature) else None
+    return FunctionFit("landmarks", xu, weights, mu, cov_func, sigma, jitter, per_feature,
+                       Lp if with_uncertainty else None, Cs, vw, cr2)
+
+
+def function_fit(x, y, landmarks=None, **kw):
+    """``FunctionEstimator.fit`` -> ``compute_conditional`` (function_estimator.py:318-420, inference.py:375-508):
+    no landmarks -> FullConditional, otherwise LandmarksConditional (there is no pre_transformation)."""
+    if landmarks is None:
+        return function_full_conditional(x, y, **kw)
+    return function_landmarks_conditional(x, landmarks, y, **kw)
+
+
+def function_leverage(fit, Xnew):
+    """``_leverage`` (conditional.py:375-400: the full predictor ignores Xnew and returns the training leverage;
+    :660-685: the landmark predictor builds B from Xnew alone)."""
+    sigma, cov_func = fit.sigma, fit.cov_func
+    p = np.shape(fit.weights)[1] if np.ndim(fit.weights) == 2 else 1
+    if fit.kind == "full":
+        K = cov_func(fit.base, fit.base)
+        if np.ndim(sigma) >= 1:
+            return np.stack([_full_leverage(K, s, fit.jitter) for s in _sigma_columns(sigma, p)], axis=1)
+        return _full_leverage(K, sigma, fit.jitter)
+    B = cov_func(ensure_2d(Xnew), fit.base)
+    K_uu = fit.L @ fit.L.T if fit.L is not None else cov_func(fit.base, fit.base)
+    if np.ndim(sigma) >= 1:
+        return np.stack([_landmark_leverage(B, K_uu, s, fit.jitter) for s in _sigma_columns(sigma, p)], axis=1)
+    return _landmark_leverage(B, K_uu, sigma, fit.jitter)
+
+
+def function_loo_residuals_squared(fit, x, y):
+    """base_predictor.py:290-325"""
+    residual = np.asarray(y, dtype=float) - conditional_mean(x, fit.base, fit.weights, fit.mu, fit.cov_func)
+    h = function_leverage(fit, x)
+    if residual.ndim > h.ndim:
+        h = h[..., None]
+    return residual ** 2 / (1 - h) ** 2
+
+
+def function_obs_variance(fit, Xnew):
+    """``_obs_variance`` (conditional.py:402-407, 687-692); variance_mu is 0."""
+    return fit.cov_func(ensure_2d(Xnew), fit.base) @ fit.variance_weights
+
+
+def function_covariance(fit, Xnew, diag=True):
+    """``_covariance`` (conditional.py:409-422, 694-717)."""
+    Xnew = ensure_2d(Xnew)
+    Kus = fit.cov_func(fit.base, Xnew)
+    A = solve_triangular(fit.L, Kus, lower=True)
+    if diag:
+        var = fit.cov_func.diag(Xnew) - np.sum(np.square(A), axis=0)
+        if fit.Cs is not None:
+            var = var + np.sum(np.square(solve_triangular(fit.Cs, Kus, lower=True)), axis=0)
+        return var
+    cov = fit.cov_func(Xnew, Xnew) - A.T @ A
+    if fit.Cs is not None:
+        C = solve_triangular(fit.Cs, Kus, lower=True)
+        cov = cov + C.T @ C
+    return cov
+
+
+# --------------------------------------------------------------------------------------
 # density_estimator.py driver (prepare_inference -> run_inference -> process_inference)
 # --------------------------------------------------------------------------------------
 FitResult = namedtuple(

@@ -39,7 +39,13 @@ def main():
     nys = mb.DensityEstimator(landmarks=lm, nn_distances=nn, rank=30)
     dens_nys = nys.fit_predict(X)
     pred_nys = nys.predict(Y)
+    # regression on the same sharded cells (FunctionEstimator, sparse conditional): two outputs, per-feature noise
+    yv = np.stack([np.sin(3 * X[:, 0]) + X[:, 1], np.cos(2 * X[:, 2])], axis=1)
+    fe = mb.FunctionEstimator(landmarks=lm, ls=0.8, sigma=np.array([0.2, 0.5]), obs_variance=True).fit(X, yv)
+    res_fe = {"fe_pred": fe.predict(Y).tolist(), "fe_lev": fe.leverage().tolist(),
+              "fe_obsvar": fe.get_obs_variance(Y).tolist()}
     res = {
+        **res_fe,
         "rank": rank, "dens": dens.tolist(), "pred": pred.tolist(), "nn": nn.tolist(),
         "std": est.pre_transformation_std.tolist(), "L_full_shape": list(np.asarray(Ld).shape),
         "dens_nys": dens_nys.tolist(), "pred_nys": pred_nys.tolist(),

@@ -219,6 +219,15 @@ class FakeLib:
         a[np.diag_indices(a.shape[0])] += v
         return 0
 
+    def mb_mat_add_diag_vec(self, ctx, h, v):
+        a = self.A(h)
+        a[np.diag_indices(a.shape[0])] += self.A(v).ravel()
+        return 0
+
+    def mb_mat_scale_rows(self, ctx, h, s):
+        self.A(h)[...] *= self.A(s).ravel()[:, None]
+        return 0
+
     def mb_mat_scale_cols(self, ctx, h, s):
         self.A(h)[...] *= self.A(s).ravel()[None, :]
         return 0

@@ -53,6 +53,13 @@ def test_sharded_fit_matches_single_process_oracle(tmp_path, world):
     Y = rng.random((203, 6))
     ref_pred = O.predict_density(ref, X, Y)
     ref_nys = O.fit_density(X, landmarks=lm, nn_distances=nn, rank=30)
+    yv = np.stack([np.sin(3 * X[:, 0]) + X[:, 1], np.cos(2 * X[:, 2])], axis=1)
+    fe = O.function_fit(X, yv, landmarks=lm, mu=0.0, cov_func=O.Matern52(0.8), sigma=np.array([0.2, 0.5]),
+                        obs_variance=True)
+    for r in res:
+        np.testing.assert_allclose(r["fe_pred"], O.conditional_mean(Y, lm, fe.weights, 0.0, fe.cov_func), rtol=1e-8)
+        np.testing.assert_allclose(r["fe_lev"], O.function_leverage(fe, X), rtol=1e-8)
+        np.testing.assert_allclose(r["fe_obsvar"], O.function_obs_variance(fe, Y), rtol=1e-7, atol=1e-10)
     for r in res:
         # every rank ends with the full, identical result
         np.testing.assert_allclose(r["nn"], nn, rtol=1e-12)

@@ -242,6 +242,28 @@ def test_gemm(be, ta, tb, m, n, k):
     assert rel_err(out, ref) < 1e-13
 
 
+@pytest.mark.parametrize("m,k", [(5, 3), (130, 77), (257, 1000)])
+def test_gemm_accumulates_into_its_output(be, m, k):
+    """``alpha A A^T + beta C`` with the operand passed twice: the landmark leverage's ``sigma^2 Lp Lp^T + B^T B``."""
+    rng = np.random.default_rng(m + k)
+    A, C0 = rng.standard_normal((m, k)), rng.standard_normal((m, m))
+    Ad = be.upload(A)
+    out = be.gemm(Ad, Ad, trans_b=True, alpha=0.37, beta=1.0, out=be.upload(C0.copy())).numpy()
+    assert rel_err(out, 0.37 * A @ A.T + C0) < 1e-13
+    out = be.gemm(Ad, be.eye(k), alpha=-2.0, beta=0.5, out=be.upload(A.copy())).numpy()
+    assert rel_err(out, -2.0 * A + 0.5 * A) < 1e-13
+
+
+@pytest.mark.parametrize("n,c", [(1, 1), (7, 3), (300, 129), (1025, 64)])
+def test_row_scaling_and_diagonal_vector(be, n, c):
+    """``mb_mat_scale_rows`` / ``mb_mat_add_diag_vec``: the per-observation noise forms of the regression path."""
+    rng = np.random.default_rng(n * 3 + c)
+    A, s = rng.standard_normal((n, c)), rng.random(n) + 0.1
+    assert np.array_equal(be.scale_rows(be.upload(A.copy(), sharded=True), s).numpy(), A * s[:, None])
+    S, v = rng.standard_normal((n, n)), rng.random(n)
+    assert np.array_equal(be.add_diag_vec(be.upload(S.copy()), v).numpy(), S + np.diag(v))
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3], ids=["dmma16w", "dfma", "dmma8w", "nosplit"])
 @pytest.mark.parametrize("n,r", [(1, 1), (50, 7), (1000, 64), (777, 130), (3000, 257), (20000, 1500)])
 def test_gram_and_ridge(be, variant, n, r):
