@@ -1,0 +1,103 @@
+"""Executable model of tools/gram_i8_proto.cu's data path (CPU, NumPy): the byte layout written by pack_kernel, the
+operand addressing of a no-swizzle K-major tcgen05 descriptor (address(row, k) = start + (row / 8) SBO + (row % 8) 16 +
+(k / 16) LBO + k % 16 — the convention tools/microbench_umma_i8.cu validated bit-exact on B200), the issuers' digit-pair
+schedule and the float64 Horner flush, transcribed index by index from the CUDA source and compared with L^T L.
+
+    python tools/gram_i8_layout_spec.py      # prints the error in units of |L|^T |L| and exits non-zero above 1e-14
+"""
+import sys
+
+import numpy as np
+
+NS, KS, TA, TB = 8, 32, 128, 64
+ASLICE, BSLICE = 2 * TA * 16, 2 * TB * 16
+ABLOCK, BBLOCK = NS * ASLICE, NS * BSLICE
+
+
+def pack(L, r):
+    rows = L.shape[0]
+    npa, nks = -(-r // TA), -(-rows // KS)
+    Ad = np.zeros(npa * nks * ABLOCK, dtype=np.int8)
+    Bd = np.zeros(2 * npa * nks * BBLOCK, dtype=np.int8)
+    scale = np.zeros(npa * TA)
+    cmax = np.max(np.abs(L), axis=0)
+    for pa in range(npa):
+        for ks in range(nks):
+            for tid in range(256):
+                col, chunk = tid & 127, tid >> 7
+                j = pa * TA + col
+                E = 0
+                if j < r:
+                    if cmax[j] > 0:
+                        E = int(np.frexp(cmax[j])[1])
+                    if ks == 0 and chunk == 0:
+                        scale[j] = np.ldexp(1.0, E - 54)
+                ab = (pa * nks + ks) * ABLOCK
+                bb = ((2 * pa + (col >> 6)) * nks + ks) * BBLOCK
+                for c in range(16):
+                    i = ks * KS + chunk * 16 + c
+                    q = 0
+                    if j < r and i < rows:
+                        q = int(np.rint(np.ldexp(L[i, j], 54 - E)))
+                    for t in range(NS - 1, -1, -1):
+                        d = ((q + 64) & 127) - 64
+                        q = (q - d) >> 7
+                        Ad[ab + t * ASLICE + chunk * (TA * 16) + col * 16 + c] = d
+                        Bd[bb + t * BSLICE + chunk * (TB * 16) + (col & 63) * 16 + c] = d
+    return Ad, Bd, scale, nks
+
+
+def operand(mem, start, lbo, sbo, nrows):
+    """The nrows x 32 int8 operand a K-major SWIZZLE_NONE descriptor addresses."""
+    out = np.empty((nrows, KS), dtype=np.int64)
+    for row in range(nrows):
+        for k in range(KS):
+            out[row, k] = mem[start + (row // 8) * sbo + (row % 8) * 16 + (k // 16) * lbo + (k % 16)]
+    return out
+
+
+def gram(L, r):
+    Ad, Bd, scale, nks = pack(L, r)
+    npa = -(-r // TA)
+    G = np.zeros((r, r))
+    for pa in range(npa):
+        for pb in range(2 * npa):
+            if not 64 * pb < 128 * (pa + 1):
+                continue
+            tmem = np.zeros((128, 512), dtype=np.int64)
+            for ks in range(nks):
+                sa, sb = (pa * nks + ks) * ABLOCK, (pb * nks + ks) * BBLOCK       # what the two bulk copies bring
+                for w in range(4):
+                    for g in (7 - w, w):
+                        for t in range(g + 1):
+                            A = operand(Ad, sa + t * ASLICE, TA * 16, 128, TA)
+                            B = operand(Bd, sb + (g - t) * BSLICE, TB * 16, 128, TB)
+                            tmem[:, g * TB:(g + 1) * TB] += A @ B.T
+            assert np.max(np.abs(tmem)) < 2 ** 31
+            for row in range(128):
+                gi = pa * TA + row
+                if gi >= r:
+                    continue
+                si = scale[gi] * 2.0 ** 49
+                for c in range(TB):
+                    gj = pb * TB + c
+                    if gj >= r:
+                        continue
+                    h = 0.0
+                    for g in range(NS):
+                        h = float(tmem[row, g * TB + c]) if g == 0 else h * 128.0 + float(tmem[row, g * TB + c])
+                    G[gi, gj] += h * si * scale[gj]
+    return G
+
+
+if __name__ == "__main__":
+    rng = np.random.default_rng(0)
+    n, r = 70, 150                                   # ragged in both directions: 3 k-steps (last one padded), 2 A panels
+    L = (rng.standard_normal((n, 1)) + 0.3 * rng.standard_normal((n, r))) * np.logspace(0, -6, r)[None, :]
+    G = gram(L, r)
+    ref = L.astype(np.longdouble).T @ L.astype(np.longdouble)
+    bound = np.abs(L).T @ np.abs(L)
+    low = np.tril_indices(r)
+    err = float(np.max(np.abs(G - ref)[low] / bound[low]))
+    print(f"gram_i8 layout model: N = {n}, R = {r}: max |G - L^T L| / (|L|^T |L|) over the lower triangle = {err:.2e}")
+    sys.exit(0 if err < 1e-14 else 1)
