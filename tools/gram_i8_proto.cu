@@ -26,8 +26,11 @@
 // 48 KB per k-step = 28 B/clk/SM from L2.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o gram_i8_proto gram_i8_proto.cu
-// Run:   timeout 120 ./gram_i8_proto [N=65536] [R=640]     (always under `timeout`: an mbarrier bug must not hang the box;
-//        every wait is bounded and reports through `status` as well)
+// Run:   timeout 120 ./gram_i8_proto [N=65536] [R=640]          Gram matrix, checked against a long-double host reference
+//        timeout 120 ./gram_i8_proto trsm [N=8192] [M=640]     X <- X Lp^-T (K3, 37 % of a step) with the same GEMM kernel:
+//                                                              left-looking over 128-column blocks, digits of X packed as
+//                                                              the blocks finish, diagonal blocks by their float64 inverses
+//        (always under `timeout`: an mbarrier bug must not hang the box; every wait is bounded and reports through `status`)
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -101,6 +104,61 @@ pack_kernel(const double* __restrict__ L, int64_t rows, int64_t r, int64_t ld, c
   }
 }
 
+// ---- pack of a row-major operand whose contraction index is the COLUMN (TRSM update): one scale per row, no transpose ----
+// block = (panel of P rows, k-step of 32 columns) -> [slice 8][k16 chunk 2][P rows][16 B]; thread = (row, chunk);
+// columns [c_lo, c_hi) only, so that X can be packed block by block as the solve finishes them.
+// `expo`: per-row exponents fixed BEFORE the values exist: |X_ij| <= |x_i| <= sqrt(k(x_i, x_i)) (Schur complement of the
+// joint kernel matrix) and |Lp_jk| <= sqrt(k(u_j, u_j) + jitter), so the product passes a constant; the test driver
+// below, whose operands are not kernel matrices, takes them from the host solution.
+template <int P>
+__global__ void __launch_bounds__(2 * P)
+pack_rows_kernel(const double* __restrict__ X, int64_t rows, int64_t cols, int64_t ld, int64_t ks_lo, int64_t ks_hi, int64_t nks,
+                 const int* __restrict__ expo, int8_t* __restrict__ Xd, double* __restrict__ scale) {
+  const int64_t panel = blockIdx.x, ks = ks_lo + blockIdx.y;
+  const int row = threadIdx.x % P, chunk = threadIdx.x / P;
+  const int64_t i = panel * P + row;
+  if (ks >= ks_hi) return;
+  int E = 0;
+  if (i < rows) {
+    E = expo[i];
+    if (blockIdx.y == 0 && chunk == 0) scale[i] = ldexp(1.0, E - 54);
+  }
+  uint32_t dig[NS][4];
+#pragma unroll
+  for (int t = 0; t < NS; t++) dig[t][0] = dig[t][1] = dig[t][2] = dig[t][3] = 0u;
+#pragma unroll
+  for (int c = 0; c < 16; c++) {
+    const int64_t k = ks * KS + chunk * 16 + c;
+    long long q = 0;
+    if (i < rows && k < cols) q = llrint(ldexp(X[i * ld + k], 54 - E));
+#pragma unroll
+    for (int t = NS - 1; t >= 0; t--) {
+      const long long d = ((q + 64) & 127) - 64;
+      q = (q - d) >> 7;
+      dig[t][c >> 2] |= (uint32_t)(uint8_t)(int8_t)d << (8 * (c & 3));
+    }
+  }
+  int8_t* blk = Xd + (panel * nks + ks) * (int64_t)(NS * 2 * P * 16);
+#pragma unroll
+  for (int t = 0; t < NS; t++)
+    *reinterpret_cast<uint4*>(blk + t * (2 * P * 16) + chunk * (P * 16) + row * 16) = make_uint4(dig[t][0], dig[t][1], dig[t][2], dig[t][3]);
+}
+
+// X[:, c0 : c0 + 128] <- X[:, c0 : c0 + 128] Tinv^T for the 128 x 128 inverse of a diagonal block of Lp (float64, one thread
+// per output; the product does this on the DMMA GEMM — 2.6 % of the solve's flops)
+__global__ void diag_solve_kernel(double* __restrict__ X, int64_t rows, int64_t ld, int64_t c0, int w, const double* __restrict__ Tinv) {
+  __shared__ double xr[128];
+  const int64_t i = blockIdx.x;
+  const int c = threadIdx.x;
+  if (c < w) xr[c] = X[i * ld + c0 + c];
+  __syncthreads();
+  if (c < w) {
+    double acc = 0.0;
+    for (int k = 0; k <= c; k++) acc = fma(xr[k], Tinv[c * 128 + k], acc);
+    X[i * ld + c0 + c] = acc;
+  }
+}
+
 // ---- tcgen05 helpers (as validated in tools/microbench_umma_i8.cu / tools/k1_i8_proto_v2.cu) --------------------------
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -150,11 +208,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t* v) {
                : "r"(taddr));
 }
 
-// ---- the GEMM: G[pa*128 .. , pb*64 ..] += (chunk of L)^T (chunk of L), lower tiles only -----------------------------------
-// tile list: blockIdx.x enumerates (pa, pb) with 64 pb < 128 (pa + 1); `tiles` holds the pairs
+// ---- the GEMM: out[pa*128 .. , pb*64 ..] += alpha A B^T for K-major digit operands A (rows_a x k) and B (rows_b x k) --------
+// Gram: A = B = (chunk of L)^T, alpha = 1, lower tiles only (`tiles` holds the (pa, pb) pairs with 64 pb < 128 (pa + 1));
+// TRSM update: A = finished columns of X (cells x k), B = Lp[block, :k], alpha = -1, out = the block of X still holding K_NM
 __global__ void __launch_bounds__(NT, 1)
-gram_i8_kernel(const int8_t* __restrict__ Ad, const int8_t* __restrict__ Bd, const double* __restrict__ scale, int64_t nks,
-               const int2* __restrict__ tiles, int64_t r, double* __restrict__ G, int64_t ldg, int* __restrict__ status) {
+gram_i8_kernel(const int8_t* __restrict__ Ad, const int8_t* __restrict__ Bd, const double* __restrict__ scale_a,
+               const double* __restrict__ scale_b, int64_t nks, int64_t a_stride_ks, int64_t b_stride_ks,
+               const int2* __restrict__ tiles, int64_t rows_a, int64_t rows_b,
+               double alpha, double* __restrict__ G, int64_t ldg, int* __restrict__ status) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t full[NST], empty[NST], done;
   __shared__ uint32_t tmem_base_sh;
@@ -178,8 +239,8 @@ gram_i8_kernel(const int8_t* __restrict__ Ad, const int8_t* __restrict__ Bd, con
   if (warp == 0) {
     // ---- producer: two bulk copies per k-step into a 4-deep ring ----
     if (lane == 0) {
-      const int8_t* asrc = Ad + (int64_t)pa * nks * ABLOCK;
-      const int8_t* bsrc = Bd + (int64_t)pb * nks * BBLOCK;
+      const int8_t* asrc = Ad + (int64_t)pa * a_stride_ks * ABLOCK;     // k-steps [0, nks) of panel pa / pb
+      const int8_t* bsrc = Bd + (int64_t)pb * b_stride_ks * BBLOCK;
       for (int64_t ks = 0; ks < nks; ks++) {
         const int s = (int)(ks % NST);
         if (ks >= NST && !mbar_wait(&empty[s], (uint32_t)(((ks / NST) - 1) & 1), status)) break;
@@ -226,7 +287,7 @@ gram_i8_kernel(const int8_t* __restrict__ Ad, const int8_t* __restrict__ Bd, con
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const int quad = warp & 3, row = quad * 32 + lane;
       const int64_t gi = (int64_t)pa * TA + row;
-      const double si = (gi < r) ? scale[gi] * 0x1p49 : 0.0;       // 128^7 of the Horner form folded into the row scale
+      const double si = (gi < rows_a) ? alpha * scale_a[gi] * 0x1p49 : 0.0;   // 128^7 of the Horner form folded into the row scale
       for (int c0 = 0; c0 < TB; c0 += 16) {
         double h[16];
 #pragma unroll
@@ -237,11 +298,11 @@ gram_i8_kernel(const int8_t* __restrict__ Ad, const int8_t* __restrict__ Bd, con
 #pragma unroll
           for (int e = 0; e < 16; e++) h[e] = (g == 0) ? (double)v[e] : fma(h[e], 128.0, (double)v[e]);
         }
-        if (gi < r) {
+        if (gi < rows_a) {
 #pragma unroll
           for (int e = 0; e < 16; e++) {
             const int64_t gj = (int64_t)pb * TB + c0 + e;
-            if (gj < r) G[gi * ldg + gj] += h[e] * si * scale[gj];
+            if (gj < rows_b) G[gi * ldg + gj] += h[e] * si * scale_b[gj];
           }
         }
       }
@@ -252,7 +313,93 @@ gram_i8_kernel(const int8_t* __restrict__ Ad, const int8_t* __restrict__ Bd, con
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
+// ---- TRSM driver: X <- X Lp^-T, left-looking over 128-column blocks; every update X_j -= X[:, :j0] Lp[j, :j0]^T on int8 slices ----
+static int run_trsm(int64_t n, int64_t m) {
+  if (n % TA || m % TA) { printf("trsm: N and M must be multiples of 128\n"); return 1; }
+  printf("TRSM int8-slice prototype: X (N=%lld x M=%lld) <- X Lp^-T, %lld column blocks\n", (long long)n, (long long)m, (long long)(m / TA));
+  // Lp = chol(I + 0.5 S), S a smooth kernel matrix on a line (well conditioned: the check is about the GEMM, not the solve)
+  std::vector<double> hK((size_t)m * m), hLp((size_t)m * m, 0.0), hC((size_t)n * m), hX((size_t)n * m);
+  for (int64_t i = 0; i < m; i++) for (int64_t j = 0; j < m; j++) {
+    const double d = (double)(i - j) / 40.0;
+    hK[(size_t)i * m + j] = (i == j ? 1.0 : 0.0) + 0.5 * exp(-0.5 * d * d);
+  }
+  for (int64_t j = 0; j < m; j++) {
+    double s = hK[(size_t)j * m + j];
+    for (int64_t k = 0; k < j; k++) s -= hLp[(size_t)j * m + k] * hLp[(size_t)j * m + k];
+    const double piv = sqrt(s);
+    hLp[(size_t)j * m + j] = piv;
+    for (int64_t i = j + 1; i < m; i++) {
+      double t = hK[(size_t)i * m + j];
+      for (int64_t k = 0; k < j; k++) t -= hLp[(size_t)i * m + k] * hLp[(size_t)j * m + k];
+      hLp[(size_t)i * m + j] = t / piv;
+    }
+  }
+  srand(5);
+  for (auto& v : hC) v = rand() / (double)RAND_MAX - 0.3;
+  for (int64_t i = 0; i < n; i++) for (int64_t j = 0; j < m; j++) {        // host reference: forward substitution per row
+    long double t = hC[(size_t)i * m + j];
+    for (int64_t k = 0; k < j; k++) t -= (long double)hX[(size_t)i * m + k] * hLp[(size_t)j * m + k];
+    hX[(size_t)i * m + j] = (double)(t / hLp[(size_t)j * m + j]);
+  }
+  // inverses of the diagonal blocks (row-major 128 x 128, lower), row exponents of both operands
+  const int64_t nb = m / TA, nks_total = m / KS;
+  std::vector<double> hTinv((size_t)nb * 128 * 128, 0.0);
+  for (int64_t b = 0; b < nb; b++) for (int c = 0; c < 128; c++) {        // column c of the inverse: solve T y = e_c
+    double* T = &hTinv[(size_t)b * 128 * 128];
+    for (int i = c; i < 128; i++) {
+      double t = (i == c) ? 1.0 : 0.0;
+      for (int k = c; k < i; k++) t -= hLp[(size_t)(b * 128 + i) * m + b * 128 + k] * T[k * 128 + c];
+      T[i * 128 + c] = t / hLp[(size_t)(b * 128 + i) * m + b * 128 + i];
+    }
+  }
+  std::vector<int> hEx(n), hEl(m);
+  for (int64_t i = 0; i < n; i++) { double mx = 0; for (int64_t j = 0; j < m; j++) mx = fmax(mx, fabs(hX[(size_t)i * m + j])); int E = 0; frexp(mx, &E); hEx[i] = E + 1; }
+  for (int64_t i = 0; i < m; i++) { double mx = 0; for (int64_t j = 0; j < m; j++) mx = fmax(mx, fabs(hLp[(size_t)i * m + j])); int E = 0; frexp(mx, &E); hEl[i] = E; }
+  double *X, *Lp, *Tinv, *sx, *sl; int8_t *Xd, *Lpd; int *ex, *el, *status; int2* tiles;
+  const int64_t npx = n / TA, npl = m / TB;
+  CK(cudaMalloc(&X, hC.size() * 8)); CK(cudaMalloc(&Lp, hLp.size() * 8)); CK(cudaMalloc(&Tinv, hTinv.size() * 8));
+  CK(cudaMalloc(&sx, n * 8)); CK(cudaMalloc(&sl, m * 8)); CK(cudaMalloc(&ex, n * 4)); CK(cudaMalloc(&el, m * 4));
+  CK(cudaMalloc(&Xd, (size_t)npx * nks_total * ABLOCK)); CK(cudaMalloc(&Lpd, (size_t)npl * nks_total * BBLOCK));
+  CK(cudaMalloc(&status, 4)); CK(cudaMemset(status, 0, 4)); CK(cudaMalloc(&tiles, 2 * npx * sizeof(int2)));
+  CK(cudaMemcpy(Lp, hLp.data(), hLp.size() * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(Tinv, hTinv.data(), hTinv.size() * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ex, hEx.data(), n * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(el, hEl.data(), m * 4, cudaMemcpyHostToDevice));
+  CK(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+  pack_rows_kernel<TB><<<dim3((unsigned)npl, (unsigned)nks_total), 2 * TB>>>(Lp, m, m, m, 0, nks_total, nks_total, el, Lpd, sl);
+  std::vector<int2> ht(2 * npx);
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 2; rep++) {
+    CK(cudaMemcpy(X, hC.data(), hC.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaEventRecord(e0));
+    for (int64_t b = 0; b < nb; b++) {
+      const int64_t j0 = b * TA;
+      if (b > 0) {
+        for (int64_t p = 0; p < npx; p++) { ht[2 * p] = make_int2((int)p, (int)(2 * b)); ht[2 * p + 1] = make_int2((int)p, (int)(2 * b + 1)); }
+        CK(cudaMemcpyAsync(tiles, ht.data(), ht.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        gram_i8_kernel<<<(unsigned)(2 * npx), NT, SMEM_TOTAL>>>(Xd, Lpd, sx, sl, j0 / KS, nks_total, nks_total, tiles, n, m, -1.0, X, m, status);
+        CK(cudaStreamSynchronize(0));                        // `ht` is reused by the next block (prototype: pageable copy)
+      }
+      diag_solve_kernel<<<(unsigned)n, 128>>>(X, n, m, j0, TA, Tinv + b * 128 * 128);
+      pack_rows_kernel<TA><<<dim3((unsigned)npx, TA / KS), 2 * TA>>>(X, n, m, m, j0 / KS, (j0 + TA) / KS, nks_total, ex, Xd, sx);
+    }
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
+  }
+  CK(cudaGetLastError());
+  int st; CK(cudaMemcpy(&st, status, 4, cudaMemcpyDeviceToHost));
+  std::vector<double> got(hC.size());
+  CK(cudaMemcpy(got.data(), X, got.size() * 8, cudaMemcpyDeviceToHost));
+  double worst = 0, big = 0;
+  for (size_t k = 0; k < got.size(); k++) { big = fmax(big, fabs(hX[k])); const double e = fabs(got[k] - hX[k]); if (e > worst || e != e) worst = e; }
+  printf("status %s; max |X - X_ref| / max |X_ref| = %.3e (float64 forward substitution in long double as reference)\n",
+         st ? "TIMEOUT in an mbarrier wait" : "ok", worst / big);
+  printf("solve %.3f ms => %.1f float64-equivalent TF/s (N M^2); scaled to N=1e6, M=5000: %.0f ms (float64 DMMA TRSM today: ~920 ms)\n",
+         best, (double)n * m * m / (best * 1e-3) * 1e-12, best * (1e6 / n) * (5000.0 / m) * (5000.0 / m));
+  return (st || !(worst / big < 1e-11)) ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && !strcmp(argv[1], "trsm")) return run_trsm(argc > 2 ? atoll(argv[2]) : 8192, argc > 3 ? atoll(argv[3]) : 640);
   const int64_t n = argc > 1 ? atoll(argv[1]) : 65536, r = argc > 2 ? atoll(argv[2]) : 640;
   const int64_t npa = (r + TA - 1) / TA, npb = 2 * npa;
   printf("Gram int8-slice prototype: N=%lld R=%lld (%lld A panels), chunk %d cells\n", (long long)n, (long long)r, (long long)npa, KC);
@@ -288,7 +435,7 @@ int main(int argc, char** argv) {
       colmax_kernel<<<dim3((unsigned)((r + 127) / 128), 64), 128>>>(L + c0 * r, rows, r, r, cmax);
       pack_kernel<<<dim3((unsigned)npa, (unsigned)nks), 256>>>(L + c0 * r, rows, r, r, cmax, nks, Ad, Bd, scale);
       CK(cudaEventRecord(b));
-      gram_i8_kernel<<<(unsigned)htiles.size(), NT, SMEM_TOTAL>>>(Ad, Bd, scale, nks, tiles, r, G, r, status);
+      gram_i8_kernel<<<(unsigned)htiles.size(), NT, SMEM_TOTAL>>>(Ad, Bd, scale, scale, nks, nks, nks, tiles, r, r, 1.0, G, r, status);
       CK(cudaEventRecord(c)); CK(cudaEventSynchronize(c));
       float x, y; CK(cudaEventElapsedTime(&x, a, b)); CK(cudaEventElapsedTime(&y, b, c)); tp += x; tg += y;
       CK(cudaEventDestroy(a)); CK(cudaEventDestroy(b)); CK(cudaEventDestroy(c));
