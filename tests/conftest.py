@@ -17,6 +17,9 @@ for p in (ROOT, os.path.dirname(os.path.abspath(__file__))):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (sm_100a) and the built libmellon_b200.so")
+    config.addinivalue_line("markers", "run_last: written after the round's GPU minutes were spent — green on the NumPy test "
+                                       "double of the ABI, not yet run on hardware; ordered after every test that has been, "
+                                       "so that `-x` cannot hide those behind a first-run surprise")
 
 
 def _have_gpu():
@@ -29,6 +32,7 @@ def _have_gpu():
 
 
 def pytest_collection_modifyitems(config, items):
+    items.sort(key=lambda item: 1 if "run_last" in item.keywords else 0)      # stable: file order otherwise kept
     if _have_gpu():
         return
     skip = pytest.mark.skip(reason="no CUDA device visible")

@@ -15,6 +15,8 @@ import pytest
 import mellon_b200 as mb
 from oracle import mellon_oracle as O
 
+pytestmark = pytest.mark.run_last
+
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_function_estimator.npz"))
 PF = np.array([0.5, 1.0, 2.0])
 CASES = {

@@ -242,6 +242,7 @@ def test_gemm(be, ta, tb, m, n, k):
     assert rel_err(out, ref) < 1e-13
 
 
+@pytest.mark.run_last
 @pytest.mark.parametrize("m,k", [(5, 3), (130, 77), (257, 1000)])
 def test_gemm_accumulates_into_its_output(be, m, k):
     """``alpha A A^T + beta C`` with the operand passed twice: the landmark leverage's ``sigma^2 Lp Lp^T + B^T B``."""
@@ -254,6 +255,7 @@ def test_gemm_accumulates_into_its_output(be, m, k):
     assert rel_err(out, -2.0 * A + 0.5 * A) < 1e-13
 
 
+@pytest.mark.run_last
 @pytest.mark.parametrize("n,c", [(1, 1), (7, 3), (300, 129), (1025, 64)])
 def test_row_scaling_and_diagonal_vector(be, n, c):
     """``mb_mat_scale_rows`` / ``mb_mat_add_diag_vec``: the per-observation noise forms of the regression path."""
