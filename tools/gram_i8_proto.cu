@@ -336,7 +336,8 @@ static int run_trsm(int64_t n, int64_t m) {
   }
   srand(5);
   for (auto& v : hC) v = rand() / (double)RAND_MAX - 0.3;
-  for (int64_t i = 0; i < n; i++) for (int64_t j = 0; j < m; j++) {        // host reference: forward substitution per row
+  const int64_t nref = n < 1024 ? n : 1024;                                // rows solved on the host: the check, and the exponents
+  for (int64_t i = 0; i < nref; i++) for (int64_t j = 0; j < m; j++) {     // host reference: forward substitution per row
     long double t = hC[(size_t)i * m + j];
     for (int64_t k = 0; k < j; k++) t -= (long double)hX[(size_t)i * m + k] * hLp[(size_t)j * m + k];
     hX[(size_t)i * m + j] = (double)(t / hLp[(size_t)j * m + j]);
@@ -353,7 +354,9 @@ static int run_trsm(int64_t n, int64_t m) {
     }
   }
   std::vector<int> hEx(n), hEl(m);
-  for (int64_t i = 0; i < n; i++) { double mx = 0; for (int64_t j = 0; j < m; j++) mx = fmax(mx, fabs(hX[(size_t)i * m + j])); int E = 0; frexp(mx, &E); hEx[i] = E + 1; }
+  int Emax = -1000;
+  for (int64_t i = 0; i < nref; i++) { double mx = 0; for (int64_t j = 0; j < m; j++) mx = fmax(mx, fabs(hX[(size_t)i * m + j])); int E = 0; frexp(mx, &E); hEx[i] = E + 1; Emax = E > Emax ? E : Emax; }
+  for (int64_t i = nref; i < n; i++) hEx[i] = Emax + 2;                    // identically distributed rows: two bits of head-room
   for (int64_t i = 0; i < m; i++) { double mx = 0; for (int64_t j = 0; j < m; j++) mx = fmax(mx, fabs(hLp[(size_t)i * m + j])); int E = 0; frexp(mx, &E); hEl[i] = E; }
   double *X, *Lp, *Tinv, *sx, *sl; int8_t *Xd, *Lpd; int *ex, *el, *status; int2* tiles;
   const int64_t npx = n / TA, npl = m / TB;
@@ -390,8 +393,9 @@ static int run_trsm(int64_t n, int64_t m) {
   std::vector<double> got(hC.size());
   CK(cudaMemcpy(got.data(), X, got.size() * 8, cudaMemcpyDeviceToHost));
   double worst = 0, big = 0;
-  for (size_t k = 0; k < got.size(); k++) { big = fmax(big, fabs(hX[k])); const double e = fabs(got[k] - hX[k]); if (e > worst || e != e) worst = e; }
-  printf("status %s; max |X - X_ref| / max |X_ref| = %.3e (float64 forward substitution in long double as reference)\n",
+  for (size_t k = 0; k < (size_t)nref * m; k++) { big = fmax(big, fabs(hX[k])); const double e = fabs(got[k] - hX[k]); if (e > worst || e != e) worst = e; }
+  for (size_t k = (size_t)nref * m; k < got.size(); k++) if (got[k] != got[k] || fabs(got[k]) > 4 * big) worst = NAN;   // unchecked rows: sane at least
+  printf("status %s; max |X - X_ref| / max |X_ref| = %.3e over the first 1024 rows (forward substitution in long double as reference)\n",
          st ? "TIMEOUT in an mbarrier wait" : "ok", worst / big);
   printf("solve %.3f ms => %.1f float64-equivalent TF/s (N M^2); scaled to N=1e6, M=5000: %.0f ms (float64 DMMA TRSM today: ~920 ms)\n",
          best, (double)n * m * m / (best * 1e-3) * 1e-12, best * (1e6 / n) * (5000.0 / m) * (5000.0 / m));
