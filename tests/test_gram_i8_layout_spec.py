@@ -44,3 +44,12 @@ def test_pack_writes_both_layouts_consistently():
         a = t * model.ASLICE + 70 * 16
         q += Ad[a:a + 16].astype(np.int64) * 128 ** (7 - t)
     np.testing.assert_allclose(q * scale[70], L[:16, 70], rtol=0, atol=2.0 ** -53 * np.max(np.abs(L[:, 70])))
+
+
+def test_trsm_model_solves_the_triangular_system():
+    """Left-looking TRSM whose block updates run through the modelled int8 GEMM on digits packed block by block."""
+    rng = np.random.default_rng(3)
+    m = 256
+    K = np.eye(m) + 0.5 * np.exp(-0.5 * ((np.arange(m)[:, None] - np.arange(m)[None, :]) / 40.0) ** 2)
+    X, ref = model.trsm(rng.random((128, m)) - 0.3, np.linalg.cholesky(K))
+    assert float(np.max(np.abs(X - ref)) / np.max(np.abs(ref))) < 1e-13

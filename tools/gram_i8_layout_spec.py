@@ -90,6 +90,83 @@ def gram(L, r):
     return G
 
 
+def pack_rows(X, expo, P, ks_lo, ks_hi, nks, Xd, scale):
+    """pack_rows_kernel<P>: digits of the columns of k-steps [ks_lo, ks_hi) of a row-major operand, one scale per row."""
+    rows, cols = X.shape
+    for panel in range(-(-rows // P)):
+        for ks in range(ks_lo, ks_hi):
+            for tid in range(2 * P):
+                row, chunk = tid % P, tid // P
+                i = panel * P + row
+                E = 0
+                if i < rows:
+                    E = int(expo[i])
+                    scale[i] = np.ldexp(1.0, E - 54)
+                blk = (panel * nks + ks) * (NS * 2 * P * 16)
+                for c in range(16):
+                    k = ks * KS + chunk * 16 + c
+                    q = 0
+                    if i < rows and k < cols:
+                        q = int(np.rint(np.ldexp(X[i, k], 54 - E)))
+                    for t in range(NS - 1, -1, -1):
+                        d = ((q + 64) & 127) - 64
+                        q = (q - d) >> 7
+                        Xd[blk + t * (2 * P * 16) + chunk * (P * 16) + row * 16 + c] = d
+
+
+def gemm_tile(Ad, Bd, scale_a, scale_b, nks, a_stride, b_stride, pa, pb, rows_a, rows_b, alpha, out):
+    """One CTA of gram_i8_kernel in its general form: out[pa*128.., pb*64..] += alpha A B^T."""
+    tmem = np.zeros((128, 512), dtype=np.int64)
+    for ks in range(nks):
+        sa, sb = (pa * a_stride + ks) * ABLOCK, (pb * b_stride + ks) * BBLOCK
+        for w in range(4):
+            for g in (7 - w, w):
+                for t in range(g + 1):
+                    A = operand(Ad, sa + t * ASLICE, TA * 16, 128, TA)
+                    B = operand(Bd, sb + (g - t) * BSLICE, TB * 16, 128, TB)
+                    tmem[:, g * TB:(g + 1) * TB] += A @ B.T
+    assert np.max(np.abs(tmem)) < 2 ** 31
+    for row in range(128):
+        gi = pa * TA + row
+        if gi >= rows_a:
+            continue
+        si = alpha * scale_a[gi] * 2.0 ** 49
+        for c in range(TB):
+            gj = pb * TB + c
+            if gj >= rows_b:
+                continue
+            h = 0.0
+            for g in range(NS):
+                h = float(tmem[row, g * TB + c]) if g == 0 else h * 128.0 + float(tmem[row, g * TB + c])
+            out[gi, gj] += h * si * scale_b[gj]
+
+
+def trsm(C, Lp):
+    """run_trsm: X <- C Lp^-T, left-looking over 128-column blocks; the update of block b is the GEMM above on the digits
+    of the finished columns of X (packed block by block) and of the rows of Lp, the diagonal block its float64 inverse."""
+    n, m = C.shape
+    assert n % TA == 0 and m % TA == 0
+    nks_total = m // KS
+    X = C.copy()
+    ref = np.linalg.solve(Lp, C.T).T
+    ex = np.frexp(np.max(np.abs(ref), axis=1))[1] + 1
+    el = np.frexp(np.max(np.abs(Lp), axis=1))[1]
+    Xd = np.zeros((n // TA) * nks_total * ABLOCK, dtype=np.int8)
+    Lpd = np.zeros((m // TB) * nks_total * BBLOCK, dtype=np.int8)
+    sx, sl = np.zeros(n), np.zeros(m)
+    pack_rows(Lp, el, TB, 0, nks_total, nks_total, Lpd, sl)
+    for b in range(m // TA):
+        j0 = b * TA
+        if b > 0:
+            for pa in range(n // TA):
+                for pb in (2 * b, 2 * b + 1):
+                    gemm_tile(Xd, Lpd, sx, sl, j0 // KS, nks_total, nks_total, pa, pb, n, m, -1.0, X)
+        Tinv = np.linalg.inv(Lp[j0:j0 + TA, j0:j0 + TA])
+        X[:, j0:j0 + TA] = X[:, j0:j0 + TA] @ np.tril(Tinv).T
+        pack_rows(X, ex, TA, j0 // KS, (j0 + TA) // KS, nks_total, Xd, sx)
+    return X, ref
+
+
 if __name__ == "__main__":
     rng = np.random.default_rng(0)
     n, r = 70, 150                                   # ragged in both directions: 3 k-steps (last one padded), 2 A panels
@@ -100,4 +177,9 @@ if __name__ == "__main__":
     low = np.tril_indices(r)
     err = float(np.max(np.abs(G - ref)[low] / bound[low]))
     print(f"gram_i8 layout model: N = {n}, R = {r}: max |G - L^T L| / (|L|^T |L|) over the lower triangle = {err:.2e}")
-    sys.exit(0 if err < 1e-14 else 1)
+    m = 256
+    K = np.eye(m) + 0.5 * np.exp(-0.5 * ((np.arange(m)[:, None] - np.arange(m)[None, :]) / 40.0) ** 2)
+    X, ref = trsm(rng.random((128, m)) - 0.3, np.linalg.cholesky(K))
+    err_t = float(np.max(np.abs(X - ref)) / np.max(np.abs(ref)))
+    print(f"trsm model: N = 128, M = {m}: max |X - C Lp^-T| / max |X| = {err_t:.2e}")
+    sys.exit(0 if err < 1e-14 and err_t < 1e-13 else 1)
