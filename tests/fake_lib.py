@@ -280,10 +280,16 @@ class FakeLib:
 
     def mb_nn_distances(self, ctx, x, allp, self_offset, dist, idx_host):
         xa, ya = self.A(x), self.A(allp)
-        d2 = ((xa[:, None, :] - ya[None, :, :]) ** 2).sum(-1)
-        d2[np.arange(xa.shape[0]), np.arange(xa.shape[0]) + self_offset] = np.inf
-        j = np.argmin(d2, axis=1)
-        self.A(dist)[:, 0] = np.sqrt(d2[np.arange(xa.shape[0]), j])
+        j = np.empty(xa.shape[0], dtype=np.int64)
+        best = np.empty(xa.shape[0])
+        for lo in range(0, xa.shape[0], 256):                     # row blocks: the difference tensor stays small
+            blk = xa[lo:lo + 256]
+            d2 = ((blk[:, None, :] - ya[None, :, :]) ** 2).sum(-1)
+            rows = np.arange(blk.shape[0])
+            d2[rows, rows + lo + self_offset] = np.inf
+            j[lo:lo + 256] = np.argmin(d2, axis=1)
+            best[lo:lo + 256] = d2[rows, j[lo:lo + 256]]
+        self.A(dist)[:, 0] = np.sqrt(best)
         if _val(idx_host):
             np.ctypeslib.as_array((C.c_int64 * xa.shape[0]).from_address(_val(idx_host)))[:] = j
         return 0
