@@ -19,8 +19,9 @@
 //                 B: [ 64-col panel][k-step           ][slice 8][k16 chunk 2][ 64 cols][16 B]   16 KB per (panel, k-step)
 //                 so one 1-D bulk copy (cp.async.bulk, >= 16 KB) fills an operand stage;
 //   gram_i8_kernel one CTA per lower 128 x 64 tile: warp 0 = producer (4-stage ring of 48 KB), warps 1-4 = MMA issuers
-//                 (issuer w owns groups w and 7 - w: 9 MMAs of 128 x 64 x 32 per k-step each, two independent
-//                 accumulation chains per thread), then the same four warps flush (tcgen05.ld lane quadrant = warp % 4).
+//                 (issuer w owns groups w and 7 - w: 9 MMAs of 128 x 64 x 32 per k-step each; ONE issuing thread sustains
+//                 only one MMA per ~144 clk whichever accumulator it targets, the rates of several issuing warps add up:
+//                 profiles/microbench_umma_i8_r01.txt), then the same four warps flush (tcgen05.ld lane quadrant = warp % 4).
 // Budget at r = 5000, N = 1e6: 1640 tiles x 31250 k-steps x 36 MMAs x 32 clk (full int8 rate) = 0.20 s on 148 SMs,
 // 0.30 s at the 5446 MAC/clk/SM measured for N = 64 tiles, against 0.85 s for the float64 DMMA SYRK; operand traffic
 // 48 KB per k-step = 28 B/clk/SM from L2.
@@ -264,8 +265,9 @@ gram_i8_kernel(const int8_t* __restrict__ Ad, const int8_t* __restrict__ Bd, con
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const uint32_t sa = s_u32(smem + s * (ABLOCK + BBLOCK)), sb = sa + ABLOCK;
         const uint32_t fresh = (ks == 0) ? 0u : 1u;
-        // the two groups' chains are interleaved so that consecutive MMAs of this thread hit different accumulators
-        // (a single accumulation chain sustains only one MMA per ~144 clk: profiles/microbench_umma_i8_r01.txt)
+        // 9 MMAs per k-step and issuer: 9 x 144 clk = 1296 clk at the measured per-thread issue rate, against 1152 clk
+        // for the k-step's 36 MMAs at the full int8 rate; the two groups are interleaved (harmless, and it keeps
+        // consecutive MMAs of one thread on different accumulators)
 #pragma unroll
         for (int t = 0; t < NS; t++) {
           if (t <= g1) {
