@@ -18,15 +18,15 @@
 //                 A: [128-col panel][k-step of 32 cells][slice 8][k16 chunk 2][128 cols][16 B]   32 KB per (panel, k-step)
 //                 B: [ 64-col panel][k-step           ][slice 8][k16 chunk 2][ 64 cols][16 B]   16 KB per (panel, k-step)
 //                 so one 1-D bulk copy (cp.async.bulk, >= 16 KB) fills an operand stage;
-//   gram_i8_kernel one CTA per lower 128 x 64 tile: warp 0 = producer (4-stage ring of 48 KB), warps 1-4 = MMA issuers
-//                 (issuer w owns groups w and 7 - w: 9 MMAs of 128 x 64 x 32 per k-step each; ONE issuing thread sustains
+//   gram_i8_kernel one CTA per lower 128 x 64 tile: warp 0 = producer (4-stage ring of 48 KB), warps 1-5 = MMA issuers
+//                 (each owns one or two digit-pair groups, at most 8 MMAs of 128 x 64 x 32 per k-step; ONE issuing thread sustains
 //                 only one MMA per ~144 clk whichever accumulator it targets, the rates of several issuing warps add up:
 //                 profiles/microbench_umma_i8_r01.txt), then the same four warps flush (tcgen05.ld lane quadrant = warp % 4).
 // Budget at r = 5000, N = 1e6: 1640 tiles x 31250 k-steps x 36 MMAs x 32 clk (full int8 rate) = 0.20 s on 148 SMs,
 // 0.30 s at the 5446 MAC/clk/SM measured for N = 64 tiles, against 0.85 s for the float64 DMMA SYRK; operand traffic
 // 48 KB per k-step = 28 B/clk/SM from L2.
 //
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o gram_i8_proto gram_i8_proto.cu
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo [-DISSUERS=4] -o gram_i8_proto gram_i8_proto.cu
 // Run:   timeout 120 ./gram_i8_proto [N=65536] [R=640]          Gram matrix, checked against a long-double host reference
 //        timeout 120 ./gram_i8_proto trsm [N=8192] [M=640]     X <- X Lp^-T (K3, 37 % of a step) with the same GEMM kernel:
 //                                                              left-looking over 128-column blocks, digits of X packed as
@@ -48,7 +48,16 @@ constexpr int TA = 128, TB = 64;               // output tile: 128 rows (A panel
 constexpr int ASLICE = 2 * TA * 16, ABLOCK = NS * ASLICE;   // 4 KB per slice, 32 KB per (A panel, k-step)
 constexpr int BSLICE = 2 * TB * 16, BBLOCK = NS * BSLICE;   // 2 KB per slice, 16 KB per (B panel, k-step)
 constexpr int NST = 4;                         // operand stages in flight
-constexpr int NISS = 4;                        // MMA-issuing warps
+#ifndef ISSUERS
+#define ISSUERS 5
+#endif
+constexpr int NISS = ISSUERS;                  // MMA-issuing warps (4 or 5; build with -DISSUERS=4 to compare)
+// digit-pair groups per issuing warp (a group g has g + 1 MMAs per k-step).  One thread issues one MMA per ~144 clk:
+//   4 warps: {0,7} {1,6} {2,5} {3,4} -> 9 MMAs each, 1296 clk per k-step;
+//   5 warps: {7} {6} {5,0} {4,1} {3,2} -> at most 8 each, 1152 clk = the k-step's 36 MMAs at the full int8 rate
+__device__ const int8_t ISSUER_GROUPS[2][5][2] = {{{0, 7}, {1, 6}, {2, 5}, {3, 4}, {-1, -1}},
+                                                 {{-1, 7}, {-1, 6}, {0, 5}, {1, 4}, {2, 3}}};
+static_assert(NISS == 4 || NISS == 5, "group tables exist for 4 and 5 issuing warps");
 constexpr int NT = (1 + NISS) * 32;            // producer warp + issuer / flush warps
 constexpr int SMEM_TOTAL = NST * (ABLOCK + BBLOCK);         // 192 KB
 constexpr int KC = 32768;                      // cells per chunk: int32 accumulators hold 8 * 4096 * 32768 = 2^30
@@ -252,12 +261,12 @@ gram_i8_kernel(const int8_t* __restrict__ Ad, const int8_t* __restrict__ Bd, con
       }
     }
   } else {
-    // ---- issuers: warp w (1..4) owns digit-pair groups g0 = w - 1 and g1 = 8 - w, accumulators at columns 64 g ----
-    const int w = warp - 1, g0 = w, g1 = 7 - w;
+    // ---- issuers: warp 1 + w owns the digit-pair groups ISSUER_GROUPS[..][w] (g0 may be absent), accumulators at columns 64 g ----
+    const int w = warp - 1, g0 = ISSUER_GROUPS[NISS - 4][w][0], g1 = ISSUER_GROUPS[NISS - 4][w][1];
     bool ok = true;
     if (lane == 0) {
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TB >> 3) << 17) | ((uint32_t)(TA >> 4) << 24);
-      const uint32_t acc0 = tmem_base + (uint32_t)(g0 * TB), acc1 = tmem_base + (uint32_t)(g1 * TB);
+      const uint32_t acc0 = tmem_base + (uint32_t)((g0 < 0 ? 0 : g0) * TB), acc1 = tmem_base + (uint32_t)(g1 * TB);
       for (int64_t ks = 0; ks < nks && ok; ks++) {
         const int s = (int)(ks % NST);
         ok = mbar_wait(&full[s], (uint32_t)((ks / NST) & 1), status);
@@ -284,8 +293,8 @@ gram_i8_kernel(const int8_t* __restrict__ Ad, const int8_t* __restrict__ Bd, con
       umma_commit(&done);
     }
     __syncwarp();
-    // ---- flush: all four warps, TMEM lane quadrant = warp % 4 (row of the tile), 16 columns at a time ----
-    if (mbar_wait(&done, 0, status, 256)) {
+    // ---- flush: warps 1-4, TMEM lane quadrant = warp % 4 (row of the tile), 16 columns at a time ----
+    if (warp <= 4 && mbar_wait(&done, 0, status, 256)) {
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const int quad = warp & 3, row = quad * 32 + lane;
       const int64_t gi = (int64_t)pa * TA + row;
