@@ -1,0 +1,327 @@
+// PROTOTYPE v3 (round-2 groundwork, not part of the product; written without GPU time left in round 1 — compiles for
+// sm_100a, NOT YET RUN): K1 (fused distance + Matern52, the headline kernel) with the contraction on tcgen05 int8 digit
+// slices, re-plumbed after what v1 / v2 and the microbenchmark measured:
+//   * ONE issuing thread sustains one MMA per ~144 clk whichever accumulator it targets, the rates of several issuing
+//     warps add up (profiles/microbench_umma_i8_r01.txt).  v2's two issuers therefore needed 36 x 144 = 5184 clk for the
+//     72 MMAs of a 128 x 64 tile, more than the 3712 clk of float64 epilogue work the tile carries.  Here FIVE warps
+//     issue (digit-pair groups {7} {6} {5,0} {4,1} {3,2}: at most 16 MMAs each per tile = 2304 clk, the full int8 rate);
+//   * all eight group accumulators of a tile are resident (8 x 64 = 512 TMEM columns), so there is no per-step hand-off:
+//     one barrier says "tile accumulated", one says "tile drained".  The eight epilogue warps first DRAIN the tile into
+//     float64 registers (tcgen05.ld, integer fold of group pairs, Horner: 32 values per thread), release TMEM at once, and
+//     only then run sqrt / exp / polynomial / stores — which overlaps the next tile's MMAs;
+//   * steady state per tile: max(MMA 2304, sqrt/exp part of the epilogue ~2700) + drain ~1000 clk = ~3700 clk, i.e. the
+//     FP64 floor of DESIGN.md §7.1: 4124 tiles per SM x 3700 clk = 7.8 ms at config 3 (v2: 31.5 ms, production DMMA
+//     kernel: 25 ms; 70 % of the HBM roofline is 8.8 ms).
+// Arithmetic, pack kernel, operand layout, descriptors and the epilogue mathematics are v2's (exact to 4.4e-16 on B200).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o k1_i8_proto_v3 k1_i8_proto_v3.cu
+// Run:   timeout 120 ./k1_i8_proto_v3 [N=131072] [M=5120]      (N multiple of 128, M multiple of 64; D = 50)
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "../mellon_b200/csrc/mb_math.cuh"
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
+
+constexpr int D = 50, KP = 64, NS = 8, TBM = 128, TBN = 64;  // features, padded k, digit slices, tile rows / columns
+constexpr int XSLICE = 4 * TBM * 16, XBLOCK = NS * XSLICE;   // cells:     [slice][4 chunks][128 rows][16 B] = 64 KB
+constexpr int YSLICE = 4 * TBN * 16, YBLOCK = NS * YSLICE;   // landmarks: [slice][4 chunks][ 64 rows][16 B] = 32 KB
+constexpr int NYB = 3;                                       // landmark tiles in flight
+constexpr int NEPI = 8, NISS = 5, EC = 32;                   // epilogue warps (1 row x 32 columns per thread), issuing warps
+constexpr int NT = (NEPI + NISS + 1) * 32;                   // + 1 producer warp = 448 threads
+constexpr int SMEM_TOTAL = XBLOCK + NYB * YBLOCK + NEPI * 32 * 8 * 8;   // operands + per-warp output staging strips (2 KB each)
+// digit-pair groups per issuing warp (group g: g + 1 digit pairs, two K = 32 MMAs each)
+__device__ const int8_t ISSUER_GROUPS[NISS][2] = {{-1, 7}, {-1, 6}, {0, 5}, {1, 4}, {2, 3}};
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ const double g_tab[64] = MB_EXP2_TABLE_INIT;
+
+// ---- pack: one thread per row -------------------------------------------------------------------------------------
+__global__ void pack_kernel(const double* __restrict__ x, int64_t n, double c, int8_t* __restrict__ digits,
+                            double* __restrict__ norm, double* __restrict__ scale, double extra_scale, int rpb) {
+  const int slice_bytes = 4 * rpb * 16;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v[D], m = 0.0;
+  for (int k = 0; k < D; k++) { v[k] = c * x[i * D + k]; m = fmax(m, fabs(v[k])); }
+  int E = 0;
+  if (m > 0.0) { frexp(m, &E); }                            // m = f 2^E, 0.5 <= f < 1  =>  |v| < 2^E
+  int8_t* blk = digits + (i / rpb) * (int64_t)(NS * slice_bytes);
+  const int r = (int)(i % rpb);
+  double nrm = 0.0;
+  for (int k = 0; k < KP; k++) {
+    long long q = 0;
+    if (k < D) q = llrint(ldexp(v[k], 54 - E));
+    const double vq = ldexp((double)q, E - 54);
+    nrm = fma(vq, vq, nrm);
+    for (int t = NS - 1; t >= 0; t--) {
+      long long d = ((q + 64) & 127) - 64;                  // balanced digit in [-64, 63]
+      q = (q - d) >> 7;
+      blk[t * slice_bytes + (k >> 4) * (rpb * 16) + r * 16 + (k & 15)] = (int8_t)d;
+    }
+  }
+  norm[i] = nrm;
+  scale[i] = ldexp(extra_scale, E - 54);
+}
+
+// ---- tcgen05 helpers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug shows up as a flag instead of a hung GPU
+// `backoff_ns` > 0: sleep between polls so that waiting warps do not take issue slots from the MMA-issuing threads
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* status, unsigned backoff_ns = 0) {
+  uint32_t ok = 0;
+  long long spins = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
+    if (!ok) {
+      if (backoff_ns) __nanosleep(backoff_ns);
+      if (++spins > 20000000LL) { atomicExch(status, 1); return; }
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(s_u32(dst)),
+               "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr));
+}
+
+// ---- the kernel -------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 1)
+k1_i8_kernel(const int8_t* __restrict__ xd, const double* __restrict__ xn, const double* __restrict__ xs, int64_t n,
+             const int8_t* __restrict__ yd, const double* __restrict__ yn, const double* __restrict__ ys, int64_t m,
+             double eps_scaled, double* __restrict__ out, int* __restrict__ status, int mode) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sx = smem;                                  // 64 KB
+  unsigned char* sy0 = smem + XBLOCK;                        // NYB x 32 KB
+  __shared__ __align__(8) uint64_t x_full, y_full[NYB], y_empty[NYB], acc_full, acc_empty;
+  __shared__ uint32_t tmem_base_sh;
+  __shared__ double tab[64];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n_ytiles = m / TBN;
+  const int64_t panel = blockIdx.x;
+
+  if (tid < 64) tab[tid] = g_tab[tid];
+  if (tid == 0) {
+    mbar_init(&x_full, 1);
+    for (int b = 0; b < NYB; b++) { mbar_init(&y_full[b], 1); mbar_init(&y_empty[b], NISS); }
+    mbar_init(&acc_full, NISS);
+    mbar_init(&acc_empty, NEPI);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(s_u32(&tmem_base_sh)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_sh;
+
+  if (warp == NEPI + NISS) {
+    // ---- TMA producer ----
+    if (lane == 0) {
+      mbar_expect_tx(&x_full, XBLOCK);
+      bulk_g2s(sx, xd + panel * (int64_t)XBLOCK, XBLOCK, &x_full);
+      for (int64_t jt = 0; jt < n_ytiles; jt++) {
+        const int b = (int)(jt % NYB);
+        if (jt >= NYB) mbar_wait(&y_empty[b], (uint32_t)(((jt / NYB) - 1) & 1), status);
+        mbar_expect_tx(&y_full[b], YBLOCK);
+        bulk_g2s(sy0 + b * YBLOCK, yd + jt * (int64_t)YBLOCK, YBLOCK, &y_full[b]);
+      }
+    }
+  } else if (warp >= NEPI) {
+    // ---- MMA issuers: warp NEPI + w owns the groups ISSUER_GROUPS[w]; accumulator of group g at TMEM columns 64 g ----
+    if (lane == 0) {
+      const int w = warp - NEPI, g0 = ISSUER_GROUPS[w][0], g1 = ISSUER_GROUPS[w][1];
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+      const uint32_t sxa = s_u32(sx);
+      const uint32_t acc0 = tmem_base + (uint32_t)((g0 < 0 ? 0 : g0) * TBN), acc1 = tmem_base + (uint32_t)(g1 * TBN);
+      mbar_wait(&x_full, 0, status);
+      for (int64_t jt = 0; jt < n_ytiles; jt++) {
+        const int b = (int)(jt % NYB);
+        mbar_wait(&y_full[b], (uint32_t)((jt / NYB) & 1), status);
+        if (jt >= 1) mbar_wait(&acc_empty, (uint32_t)((jt - 1) & 1), status);   // the previous tile has left TMEM
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t sya = s_u32(sy0 + b * YBLOCK);
+#pragma unroll
+        for (int t = 0; t < NS; t++) {
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const uint64_t da = make_desc(sxa + t * XSLICE + (2 * h) * (TBM * 16), TBM * 16, 128);
+            if (t <= g1)
+              umma_i8(acc1, da, make_desc(sya + (g1 - t) * YSLICE + (2 * h) * (TBN * 16), TBN * 16, 128), idesc, (t | h) ? 1u : 0u);
+            if (t <= g0)
+              umma_i8(acc0, da, make_desc(sya + (g0 - t) * YSLICE + (2 * h) * (TBN * 16), TBN * 16, 128), idesc, (t | h) ? 1u : 0u);
+          }
+        }
+        umma_commit(&y_empty[b]);   // landmark buffer b may be refilled once this issuer's MMAs have read it
+        umma_commit(&acc_full);     // ... and its groups of this tile are complete
+      }
+    }
+  } else {
+    // ---- epilogue warps: TMEM lane quadrant = warp % 4 (rows), 32-column half = warp / 4 ----
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
+    const int64_t grow = panel * TBM + row;
+    const double xn_i = xn[grow] + eps_scaled, xs_i = xs[grow];
+    double* stage = reinterpret_cast<double*>(smem + XBLOCK + NYB * YBLOCK) + warp * (32 * 8);
+    for (int64_t jt = 0; jt < n_ytiles; jt++) {
+      mbar_wait(&acc_full, (uint32_t)(jt & 1), status, 64);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      // drain: 32 columns of this thread's row, all eight groups, folded to one float64 each
+      double acc[EC];
+#pragma unroll
+      for (int c0 = 0; c0 < EC; c0 += 16) {
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+          const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((2 * s) * TBN + half * EC + c0);
+          int32_t ge[16], go[16];
+          tmem_ld16(ta, ge);
+          tmem_ld16(ta + TBN, go);
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const double hh = (double)(ge[j] * 128 + go[j]);          // |G| <= 8 * 64 * 4096 = 2^21: the pair fits int32
+            acc[c0 + j] = (s == 0) ? hh : fma(acc[c0 + j], 16384.0, hh);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty);      // TMEM is free: the next tile's MMAs run under the code below
+      const int64_t col0 = jt * TBN + half * EC;
+      double* obase = out + (panel * TBM + quad * 32) * m + col0;
+#pragma unroll
+      for (int j0 = 0; j0 < EC; j0 += 8) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          const double dot = acc[j0 + e] * xs_i * ys[col0 + j0 + e];
+          double sq = fma(-2.0, dot, xn_i + yn[col0 + j0 + e]);
+          sq = mbmath::clamp_tiny(sq);
+          double kvv = sq;
+          if (!(mode & 1)) {
+            const double r = mbmath::sqrt_pos(sq);
+            const double ex = mbmath::exp_neg(r, tab);
+            kvv = fma(fma(r, 1.0 / 3.0, 1.0), r, 1.0) * ex;
+          }
+          stage[lane * 8 + (e ^ (lane & 7))] = kvv;
+        }
+        __syncwarp();
+        if (!(mode & 4)) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int rr = q * 8 + (lane >> 2), cc = (lane & 3) * 2;
+            const double v0 = stage[rr * 8 + (cc ^ (rr & 7))], v1 = stage[rr * 8 + ((cc + 1) ^ (rr & 7))];
+            *reinterpret_cast<double2*>(obase + (int64_t)rr * m + j0 + cc) = make_double2(v0, v1);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+int main(int argc, char** argv) {
+  const int64_t n = argc > 1 ? atoll(argv[1]) : 131072, m = argc > 2 ? atoll(argv[2]) : 5120;
+  if (n % TBM || m % TBN) { printf("N must be a multiple of 128, M of 64\n"); return 1; }
+  const double ls = 38.0, c = sqrt(5.0) / ls;
+  printf("K1 int8-slice prototype v3: N=%lld M=%lld D=%d Matern52 ls=%g\n", (long long)n, (long long)m, D, ls);
+  std::vector<double> hx((size_t)n * D), hy((size_t)m * D);
+  srand(7);
+  for (auto& v : hx) v = rand() / (double)RAND_MAX;
+  for (auto& v : hy) v = rand() / (double)RAND_MAX;
+  double *x, *y, *xn, *xs, *yn, *ys, *out; int8_t *xd, *yd; int* status;
+  CK(cudaMalloc(&x, hx.size() * 8)); CK(cudaMalloc(&y, hy.size() * 8));
+  CK(cudaMalloc(&xd, (n / TBM) * (size_t)XBLOCK)); CK(cudaMalloc(&yd, (m / TBN) * (size_t)YBLOCK));
+  CK(cudaMalloc(&xn, n * 8)); CK(cudaMalloc(&xs, n * 8)); CK(cudaMalloc(&yn, m * 8)); CK(cudaMalloc(&ys, m * 8));
+  CK(cudaMalloc(&out, (size_t)n * m * 8)); CK(cudaMalloc(&status, 4)); CK(cudaMemset(status, 0, 4));
+  CK(cudaMemcpy(x, hx.data(), hx.size() * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(y, hy.data(), hy.size() * 8, cudaMemcpyHostToDevice));
+  CK(cudaFuncSetAttribute(k1_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+  cudaEvent_t e0, e1, e2; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
+  float ms_pack = 0, ms_k = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    CK(cudaEventRecord(e0));
+    pack_kernel<<<(unsigned)((n + 127) / 128), 128>>>(x, n, c, xd, xn, xs, 1.0, TBM);
+    pack_kernel<<<(unsigned)((m + 127) / 128), 128>>>(y, m, c, yd, yn, ys, ldexp(1.0, 49), TBN);   // 128^7 folded into the landmark scale
+    CK(cudaEventRecord(e1));
+    k1_i8_kernel<<<(unsigned)(n / TBM), NT, SMEM_TOTAL>>>(xd, xn, xs, n, yd, yn, ys, m, 1e-12 * c * c, out, status, 0);
+    CK(cudaEventRecord(e2)); CK(cudaEventSynchronize(e2));
+    float a, b; CK(cudaEventElapsedTime(&a, e0, e1)); CK(cudaEventElapsedTime(&b, e1, e2));
+    ms_pack = a; if (b < ms_k) ms_k = b;
+  }
+  CK(cudaGetLastError());
+  int st; CK(cudaMemcpy(&st, status, 4, cudaMemcpyDeviceToHost));
+  // check: first 128 x 256 block and the last 64 rows against the host double-precision reference
+  std::vector<double> hout;
+  double maxerr = 0; long bad = 0;
+  auto check_rows = [&](int64_t r0, int64_t nr, int64_t c0, int64_t nc) {
+    hout.resize((size_t)nr * m);
+    CK(cudaMemcpy(hout.data(), out + r0 * m, (size_t)nr * m * 8, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < nr; i++) for (int64_t j = c0; j < c0 + nc; j++) {
+      double xx = 0, yy = 0, xy = 0;
+      for (int k = 0; k < D; k++) { const double a = hx[(r0 + i) * D + k], b = hy[j * D + k]; xx += a * a; yy += b * b; xy += a * b; }
+      const double sq = fmax(xx - 2 * xy + yy + 1e-12, 0.0), r = sqrt(5.0) * sqrt(sq) / ls;
+      const double ref = (r + r * r / 3.0 + 1.0) * exp(-r);
+      const double err = fabs(hout[(size_t)i * m + j] - ref);
+      if (!(err < 1e-12)) bad++;
+      if (err > maxerr || err != err) maxerr = err;
+    }
+  };
+  check_rows(0, 128, 0, 256 < m ? 256 : m);
+  check_rows(n - 64, 64, m - 128, 128);
+  const double bytes = 8.0 * ((double)n * m + (double)(n + m) * D);
+  printf("status %s; max |K - K_ref| = %.3e (%ld entries above 1e-12)\n", st ? "TIMEOUT in an mbarrier wait" : "ok", maxerr, bad);
+  printf("pack %.3f ms, kernel %.3f ms => %.1f GB/s algorithmic (kernel only), %.1f GB/s with the pack pass\n", ms_pack, ms_k,
+         bytes / ms_k * 1e-6, bytes / (ms_k + ms_pack) * 1e-6);
+  printf("scaled to N=1e6, M=5000: kernel %.2f ms, pack %.2f ms\n", ms_k * (1e6 * 5000.0) / ((double)n * m), ms_pack * 1e6 / n);
+  // timing decomposition (results of these runs are not checked)
+  for (int mode : {1, 4, 5}) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 2; rep++) {
+      CK(cudaEventRecord(e1));
+      k1_i8_kernel<<<(unsigned)(n / TBM), NT, SMEM_TOTAL>>>(xd, xn, xs, n, yd, yn, ys, m, 1e-12 * c * c, out, status, mode);
+      CK(cudaEventRecord(e2)); CK(cudaEventSynchronize(e2));
+      float b; CK(cudaEventElapsedTime(&b, e1, e2)); if (b < best) best = b;
+    }
+    printf("mode %d (%s%s): kernel %.3f ms\n", mode, (mode & 1) ? "no sqrt/exp/poly " : "", (mode & 4) ? "no stores" : "", best);
+  }
+  return 0;
+}

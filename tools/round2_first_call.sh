@@ -33,7 +33,17 @@ for args in "1024 256" "8192 640" "131072 2560"; do
   echo "exit $?" >> "$OUT/gram_i8_proto.txt"
 done
 
+# 2b. K1 on int8 slices, v3 (five issuing warps, drain-then-compute epilogue) next to v2 for the before / after
+(cd tools && $NVCC -o k1_i8_proto_v3 k1_i8_proto_v3.cu && $NVCC -o k1_i8_proto_v2 k1_i8_proto_v2.cu) >> "$OUT/build.txt" 2>&1
+for exe in k1_i8_proto_v3 k1_i8_proto_v2; do
+  echo "== $exe 131072 5120" >> "$OUT/k1_i8_proto.txt"
+  timeout 120 tools/$exe 131072 5120 >> "$OUT/k1_i8_proto.txt" 2>&1
+  echo "exit $?" >> "$OUT/k1_i8_proto.txt"
+done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k1_i8_kernel -c 1 -o "$OUT/k1_i8_proto_v3" \
+  tools/k1_i8_proto_v3 131072 5120 > "$OUT/ncu_k1.txt" 2>&1
+
 # 3. one ncu capture of the prototype GEMM at the timing size (tensor pipe, L2 / DRAM traffic, stall reasons)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gram_i8_kernel -c 1 -o "$OUT/gram_i8_proto" \
   tools/gram_i8_proto 65536 5000 > "$OUT/ncu.txt" 2>&1
-tail -5 "$OUT/pytest_new.txt" "$OUT/pytest_gpu.txt" "$OUT/gram_i8_proto.txt"
+tail -5 "$OUT/pytest_new.txt" "$OUT/pytest_gpu.txt" "$OUT/gram_i8_proto.txt" "$OUT/k1_i8_proto.txt"
