@@ -3,13 +3,15 @@
 // slices, re-plumbed after what v1 / v2 and the microbenchmark measured:
 //   * ONE issuing thread sustains one MMA per ~144 clk whichever accumulator it targets, the rates of several issuing
 //     warps add up (profiles/microbench_umma_i8_r01.txt).  v2's two issuers therefore needed 36 x 144 = 5184 clk for the
-//     72 MMAs of a 128 x 64 tile, more than the 3712 clk of float64 epilogue work the tile carries.  Here FIVE warps
-//     issue (digit-pair groups {7} {6} {5,0} {4,1} {3,2}: at most 16 MMAs each per tile = 2304 clk, the full int8 rate);
+//     72 MMAs of a 128 x 64 tile, more than the 3712 clk of float64 epilogue work the tile carries.  Here FOUR warps
+//     issue (digit-pair groups {0,7} {1,6} {2,5} {3,4}: 18 MMAs each per tile = 2592 clk; a fifth would reach the full
+//     int8 rate but push the CTA from 12 to 16 allocated warps, i.e. from 168 to 128 registers per thread — the epilogue
+//     wants the registers more); the first of them also feeds the landmark ring;
 //   * all eight group accumulators of a tile are resident (8 x 64 = 512 TMEM columns), so there is no per-step hand-off:
 //     one barrier says "tile accumulated", one says "tile drained".  The eight epilogue warps first DRAIN the tile into
 //     float64 registers (tcgen05.ld, integer fold of group pairs, Horner: 32 values per thread), release TMEM at once, and
 //     only then run sqrt / exp / polynomial / stores — which overlaps the next tile's MMAs;
-//   * steady state per tile: max(MMA 2304, sqrt/exp part of the epilogue ~2700) + drain ~1000 clk = ~3700 clk, i.e. the
+//   * steady state per tile: max(MMA 2592, sqrt/exp part of the epilogue ~2700) + drain ~1000 clk = ~3700 clk, i.e. the
 //     FP64 floor of DESIGN.md §7.1: 4124 tiles per SM x 3700 clk = 7.8 ms at config 3 (v2: 31.5 ms, production DMMA
 //     kernel: 25 ms; 70 % of the HBM roofline is 8.8 ms).
 // Arithmetic, pack kernel, operand layout, descriptors and the epilogue mathematics are v2's (exact to 4.4e-16 on B200).
@@ -31,11 +33,12 @@ constexpr int D = 50, KP = 64, NS = 8, TBM = 128, TBN = 64;  // features, padded
 constexpr int XSLICE = 4 * TBM * 16, XBLOCK = NS * XSLICE;   // cells:     [slice][4 chunks][128 rows][16 B] = 64 KB
 constexpr int YSLICE = 4 * TBN * 16, YBLOCK = NS * YSLICE;   // landmarks: [slice][4 chunks][ 64 rows][16 B] = 32 KB
 constexpr int NYB = 3;                                       // landmark tiles in flight
-constexpr int NEPI = 8, NISS = 5, EC = 32;                   // epilogue warps (1 row x 32 columns per thread), issuing warps
-constexpr int NT = (NEPI + NISS + 1) * 32;                   // + 1 producer warp = 448 threads
+constexpr int NEPI = 8, NISS = 4, EC = 32;                   // epilogue warps (1 row x 32 columns per thread), issuing warps
+constexpr int NT = (NEPI + NISS) * 32;                       // 384 threads: 12 warps leave 168 registers per thread (16 would leave 128);
+                                                             // the first issuing thread also feeds the landmark ring
 constexpr int SMEM_TOTAL = XBLOCK + NYB * YBLOCK + NEPI * 32 * 8 * 8;   // operands + per-warp output staging strips (2 KB each)
 // digit-pair groups per issuing warp (group g: g + 1 digit pairs, two K = 32 MMAs each)
-__device__ const int8_t ISSUER_GROUPS[NISS][2] = {{-1, 7}, {-1, 6}, {0, 5}, {1, 4}, {2, 3}};
+__device__ const int8_t ISSUER_GROUPS[NISS][2] = {{0, 7}, {1, 6}, {2, 5}, {3, 4}};
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ const double g_tab[64] = MB_EXP2_TABLE_INIT;
@@ -152,30 +155,33 @@ k1_i8_kernel(const int8_t* __restrict__ xd, const double* __restrict__ xn, const
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = tmem_base_sh;
 
-  if (warp == NEPI + NISS) {
-    // ---- TMA producer ----
-    if (lane == 0) {
-      mbar_expect_tx(&x_full, XBLOCK);
-      bulk_g2s(sx, xd + panel * (int64_t)XBLOCK, XBLOCK, &x_full);
-      for (int64_t jt = 0; jt < n_ytiles; jt++) {
-        const int b = (int)(jt % NYB);
-        if (jt >= NYB) mbar_wait(&y_empty[b], (uint32_t)(((jt / NYB) - 1) & 1), status);
-        mbar_expect_tx(&y_full[b], YBLOCK);
-        bulk_g2s(sy0 + b * YBLOCK, yd + jt * (int64_t)YBLOCK, YBLOCK, &y_full[b]);
-      }
-    }
-  } else if (warp >= NEPI) {
+  if (warp >= NEPI) {
     // ---- MMA issuers: warp NEPI + w owns the groups ISSUER_GROUPS[w]; accumulator of group g at TMEM columns 64 g ----
     if (lane == 0) {
       const int w = warp - NEPI, g0 = ISSUER_GROUPS[w][0], g1 = ISSUER_GROUPS[w][1];
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
       const uint32_t sxa = s_u32(sx);
       const uint32_t acc0 = tmem_base + (uint32_t)((g0 < 0 ? 0 : g0) * TBN), acc1 = tmem_base + (uint32_t)(g1 * TBN);
+      if (w == 0) {                                           // producer duty: cell panel + the first landmark tiles
+        mbar_expect_tx(&x_full, XBLOCK);
+        bulk_g2s(sx, xd + panel * (int64_t)XBLOCK, XBLOCK, &x_full);
+        for (int64_t jt = 0; jt < NYB && jt < n_ytiles; jt++) {
+          mbar_expect_tx(&y_full[jt], YBLOCK);
+          bulk_g2s(sy0 + jt * YBLOCK, yd + jt * (int64_t)YBLOCK, YBLOCK, &y_full[jt]);
+        }
+      }
       mbar_wait(&x_full, 0, status);
       for (int64_t jt = 0; jt < n_ytiles; jt++) {
         const int b = (int)(jt % NYB);
         mbar_wait(&y_full[b], (uint32_t)((jt / NYB) & 1), status);
         if (jt >= 1) mbar_wait(&acc_empty, (uint32_t)((jt - 1) & 1), status);   // the previous tile has left TMEM
+        if (w == 0 && jt >= 1 && jt - 1 + NYB < n_ytiles) {
+          // tile jt - 1 is drained, so every MMA that read its landmark buffer has completed: refill it (the wait returns at once)
+          const int pb = (int)((jt - 1) % NYB);
+          mbar_wait(&y_empty[pb], (uint32_t)(((jt - 1) / NYB) & 1), status);
+          mbar_expect_tx(&y_full[pb], YBLOCK);
+          bulk_g2s(sy0 + pb * YBLOCK, yd + (jt - 1 + NYB) * (int64_t)YBLOCK, YBLOCK, &y_full[pb]);
+        }
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const uint32_t sya = s_u32(sy0 + b * YBLOCK);
 #pragma unroll
@@ -203,22 +209,26 @@ k1_i8_kernel(const int8_t* __restrict__ xd, const double* __restrict__ xn, const
     for (int64_t jt = 0; jt < n_ytiles; jt++) {
       mbar_wait(&acc_full, (uint32_t)(jt & 1), status, 64);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      // drain: 32 columns of this thread's row, all eight groups, folded to one float64 each
+      // drain: 32 columns of this thread's row, all eight groups, folded to one float64 each.  Eight units of
+      // (16 columns) x (group pair 2s, 2s + 1); the loads of unit u + 1 are in flight while unit u is folded
       double acc[EC];
+      int32_t ge[2][16], go[2][16];
+      const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * EC);
+      tmem_ld16(tbase, ge[0]);
+      tmem_ld16(tbase + TBN, go[0]);
 #pragma unroll
-      for (int c0 = 0; c0 < EC; c0 += 16) {
+      for (int u = 0; u < 8; u++) {
+        const int c0 = (u >> 2) * 16, s = u & 3;
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        if (u + 1 < 8) {
+          const uint32_t ta = tbase + (uint32_t)((2 * ((u + 1) & 3)) * TBN + ((u + 1) >> 2) * 16);
+          tmem_ld16(ta, ge[(u + 1) & 1]);
+          tmem_ld16(ta + TBN, go[(u + 1) & 1]);
+        }
 #pragma unroll
-        for (int s = 0; s < 4; s++) {
-          const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((2 * s) * TBN + half * EC + c0);
-          int32_t ge[16], go[16];
-          tmem_ld16(ta, ge);
-          tmem_ld16(ta + TBN, go);
-          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-          for (int j = 0; j < 16; j++) {
-            const double hh = (double)(ge[j] * 128 + go[j]);          // |G| <= 8 * 64 * 4096 = 2^21: the pair fits int32
-            acc[c0 + j] = (s == 0) ? hh : fma(acc[c0 + j], 16384.0, hh);
-          }
+        for (int j = 0; j < 16; j++) {
+          const double hh = (double)(ge[u & 1][j] * 128 + go[u & 1][j]);   // |G| <= 8 * 64 * 4096 = 2^21: the pair fits int32
+          acc[c0 + j] = (s == 0) ? hh : fma(acc[c0 + j], 16384.0, hh);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
