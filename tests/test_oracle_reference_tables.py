@@ -209,3 +209,20 @@ def test_exponential_and_ratquad_conventions():
     assert O.RatQuad(3.0, 2.0)(x, y)[0, 0] == pytest.approx((d * d / 4 / 6 + 1) ** -3.0, rel=1e-14)
     assert O.Matern52(1.0)(x, x)[0, 0] < 1.0  # distance(x, x) = 1e-6, not 0
     assert O.distance(x, x)[0, 0] == pytest.approx(1e-6)
+
+
+def test_fast_quantile_is_numpy_quantile_bit_for_bit():
+    """compute_mu's percentile (parameters.py:586-599) comes from one selection instead of np.quantile's three: same bits."""
+    from mellon_b200.parameters import _quantile_linear, compute_mu
+
+    rng = np.random.default_rng(11)
+    for trial in range(40):
+        a = rng.standard_normal(int(rng.integers(4096, 60000))) * 10 ** rng.uniform(-3, 3)
+        if trial % 5 == 0:
+            a = np.round(a, 1)                                   # ties around the order statistic
+        for q in (0.01, 0.5, 0.37, 0.999, 0.0, 1.0):
+            assert _quantile_linear(a, q) == np.quantile(a, q)
+    a[5] = np.nan
+    assert np.isnan(_quantile_linear(a, 0.01))
+    nn = rng.random(50000) * 0.3 + 0.01
+    assert compute_mu(nn, 7) == O.compute_mu(nn, 7)
