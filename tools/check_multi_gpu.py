@@ -37,7 +37,12 @@ def main():
     pred = est.predict(Y)
     nys = mb.DensityEstimator(landmarks=lm, nn_distances=nn, rank=200, check_rank=False)
     dens_nys = nys.fit_predict(X)
-    digest = hashlib.sha256(dens.tobytes() + pred.tobytes() + dens_nys.tobytes()).hexdigest()
+    # regression on the same sharded cells (FunctionEstimator, sparse conditional, per-feature noise, observation variance)
+    yv = np.stack([np.sin(3 * X[:, 0]) + X[:, 1], np.cos(2 * X[:, 2])], axis=1)
+    fe = mb.FunctionEstimator(landmarks=lm, ls=0.8, sigma=np.array([0.2, 0.5]), obs_variance=True).fit(X, yv)
+    fe_pred, fe_lev, fe_var = fe.predict(Y), fe.leverage(), fe.get_obs_variance(Y)
+    digest = hashlib.sha256(dens.tobytes() + pred.tobytes() + dens_nys.tobytes() + fe_pred.tobytes() + fe_lev.tobytes()
+                            + fe_var.tobytes()).hexdigest()
     import torch
     import torch.distributed as td
 
@@ -51,7 +56,12 @@ def main():
         ref = O.fit_density(X, landmarks=lm, nn_distances=nn_ref)
         ref_pred = O.predict_density(ref, X, Y)
         ref_nys = O.fit_density(X, landmarks=lm, nn_distances=nn_ref, rank=200)
+        fo = O.function_fit(X, yv, landmarks=lm, mu=0.0, cov_func=O.Matern52(0.8), sigma=np.array([0.2, 0.5]), obs_variance=True)
+        amax = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(np.asarray(b))))
         errs = {
+            "function_predict": amax(fe_pred, O.conditional_mean(Y, lm, fo.weights, 0.0, fo.cov_func)),
+            "function_leverage": amax(fe_lev, O.function_leverage(fo, X)),
+            "function_obs_variance": amax(fe_var, O.function_obs_variance(fo, Y)),
             "nn_distances": rel(nn, nn_ref),
             "log_density": rel(dens, ref.log_density_x),
             "predict": rel(pred, ref_pred),
@@ -61,7 +71,8 @@ def main():
         }
         print(f"world={world} identical_bits_on_all_ranks={same} nfev={est.opt_state.num_fun_eval} errors={errs}")
         ok = same and errs["nn_distances"] < 1e-12 and errs["log_density"] < 1e-5 and errs["predict"] < 1e-5 \
-            and errs["nystroem_log_density"] < 1e-5
+            and errs["nystroem_log_density"] < 1e-5 and errs["function_predict"] < 1e-6 and errs["function_leverage"] < 1e-6 \
+            and errs["function_obs_variance"] < 1e-6
         print("MULTI_GPU_PARITY", "OK" if ok else "FAILED")
     dist.barrier()
 
