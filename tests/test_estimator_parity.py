@@ -56,7 +56,7 @@ def test_config1_readme_smoke_full_gp(be):
     ref = O.fit_density(X)
     assert est.gp_type == mb.util.GaussianProcessType.FULL and est.landmarks is None
     assert dens.shape == (100,)
-    assert est.mu == pytest.approx(ref.mu, rel=1e-14) and est.ls == pytest.approx(ref.ls, rel=1e-14)
+    assert est.mu == pytest.approx(ref.mu, rel=1e-13) and est.ls == pytest.approx(ref.ls, rel=1e-13)
     assert rel(dens, ref.log_density_x) < TOL
     # predict(X) reproduces fit_predict(X) (tests/test_density_estimator.py:30-44)
     # jitter makes the interpolation inexact: K (K + 1e-6 I)^-1 f != f; same deviation on both sides
@@ -173,7 +173,13 @@ def test_default_landmarks_kmeans_identical_on_both_sides(be, tight):
     np.testing.assert_allclose(lm, ref.landmarks, rtol=1e-12, atol=1e-12)
     assign = lambda c: np.argmin(((X[:, None, :] - c[None]) ** 2).sum(-1), axis=1)
     assert np.array_equal(assign(lm), assign(ref.landmarks))
-    assert np.array_equal(np.asarray(est.nn_distances), ref.nn_distances)  # bit-exact neighbour selection
+    # neighbour SELECTION is bit-exact (the device search picks the neighbours the exact search picks); the distance
+    # itself comes from a warp-parallel fused sum on the device, i.e. the same number up to the last bits
+    from sklearn.neighbors import NearestNeighbors
+
+    _, idx = be.nn_distances(X, return_index=True)
+    assert np.array_equal(idx, NearestNeighbors(n_neighbors=2, algorithm="brute").fit(X).kneighbors(X)[1][:, 1])
+    np.testing.assert_allclose(np.asarray(est.nn_distances), ref.nn_distances, rtol=1e-13)
     ref = O.fit_density(X, landmarks=lm, nn_distances=ref.nn_distances, lbfgsb_options=tight)
     assert rel(dens, ref.log_density_x) < TIGHT_TOL
 
@@ -218,7 +224,7 @@ def test_time_sensitive_estimator(be, tight):
     for t in range(T):
         mask = times == t
         nn[mask] = O.compute_nn_distances(X[mask])
-    np.testing.assert_array_equal(est.nn_distances, nn)
+    np.testing.assert_allclose(est.nn_distances, nn, rtol=1e-13)     # device search per time point vs the exact host search
     cov = O.Matern52(1.5, active_dims=slice(None, -1)) * O.Matern52(0.8, active_dims=-1)
     ref = O.fit_density(Xt, cov_func=cov, landmarks=lm, nn_distances=nn, d=d, ls=1.5, lbfgsb_options=tight)
     assert rel(dens, ref.log_density_x) < TOL
