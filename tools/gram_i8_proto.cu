@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(NT, 1)
 gram_i8_kernel(const int8_t* __restrict__ Ad, const int8_t* __restrict__ Bd, const double* __restrict__ scale_a,
                const double* __restrict__ scale_b, int64_t nks, int64_t a_stride_ks, int64_t b_stride_ks,
                const int2* __restrict__ tiles, int64_t rows_a, int64_t rows_b,
-               double alpha, double* __restrict__ G, int64_t ldg, int* __restrict__ status) {
+               double alpha, double* __restrict__ G, int64_t ldg, int* __restrict__ status, int mode = 0) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t full[NST], empty[NST], done;
   __shared__ uint32_t tmem_base_sh;
@@ -277,8 +277,9 @@ gram_i8_kernel(const int8_t* __restrict__ Ad, const int8_t* __restrict__ Bd, con
         // 9 MMAs per k-step and issuer: 9 x 144 clk = 1296 clk at the measured per-thread issue rate, against 1152 clk
         // for the k-step's 36 MMAs at the full int8 rate; the two groups are interleaved (harmless, and it keeps
         // consecutive MMAs of one thread on different accumulators)
+        // mode 1 (timing decomposition): the operand ring runs, no MMA is issued — what the copies alone cost
 #pragma unroll
-        for (int t = 0; t < NS; t++) {
+        for (int t = 0; t < NS && !(mode & 1); t++) {
           if (t <= g1) {
             umma_i8(acc1, make_desc(sa + t * ASLICE, TA * 16, 128), make_desc(sb + (g1 - t) * BSLICE, TB * 16, 128), idesc,
                     (t == 0) ? fresh : 1u);
@@ -478,5 +479,14 @@ int main(int argc, char** argv) {
          ms_pack, ms_gemm, macs / (ms_gemm * 1e-3) / (148 * 1.965e9), (double)n * r * r / ((ms_gemm + ms_pack) * 1e-3) * 1e-12);
   printf("scaled to N=1e6, R=5000: gemm %.0f ms, pack %.0f ms (float64 DMMA SYRK today: ~850 ms)\n",
          ms_gemm * (1e6 / n) * (1640.0 / htiles.size()), ms_pack * (1e6 / n) * (5000.0 / r));
+  {  // timing decomposition on the last chunk's operands (result not checked): operand ring only, no MMAs
+    const int64_t rows = (n % KC) ? (n % KC) : (n < KC ? n : KC), nks = (rows + KS - 1) / KS;
+    float ms = 0;
+    CK(cudaEventRecord(e0));
+    gram_i8_kernel<<<(unsigned)htiles.size(), NT, SMEM_TOTAL>>>(Ad, Bd, scale, scale, nks, nks, nks, tiles, r, r, 1.0, G, r, status, 1);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("mode 1 (operand ring only, one chunk of %lld cells): %.3f ms = %.1f B/clk/SM\n", (long long)rows, ms,
+           (double)htiles.size() * nks * (ABLOCK + BBLOCK) / (ms * 1e-3) / (148 * 1.965e9));
+  }
   return 0;
 }
