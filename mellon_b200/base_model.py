@@ -86,6 +86,7 @@ class BaseEstimator:
         self.jit = validate_bool(jit, "jit")
         self.check_rank = validate_bool(check_rank, "check_rank", optional=True)
         self.x = None
+        self._x_given = None
         self.pre_transformation = None
 
     def __str__(self):
@@ -130,12 +131,16 @@ class BaseEstimator:
     def set_x(self, x):
         """Validate and store the training instances (``base_model.py:176-213``).  Passing a
         different object than the one already set raises — identity, not equality."""
-        if self.x is not None and x is not None and self.x is not x:
+        if self.x is not None and x is not None and self.x is not x and getattr(self, "_x_given", None) is not x:
             self._fail("self.x has been set already, but is not equal to the argument x.")
         if self.x is None and x is None:
             self._fail("Required argument x is missing and self.x has not been set.")
         if x is None:
             x = self.x
+        elif x is not self.x:
+            # validation turns ndarray subclasses / foreign array types into a NEW float64 array; remember the object
+            # the caller passed, so that passing it again is still "the same x" as in the reference (jnp.asarray keeps it)
+            self._x_given = x
         self.x = validate_array(x, "x")
         return self.x
 

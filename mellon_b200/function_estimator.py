@@ -103,11 +103,12 @@ class FunctionEstimator(BaseEstimator):
 
     def compute_conditional(self, x=None, y=None, obs_variance=None):
         """Condition the GP on ``y`` observed at ``x`` (``function_estimator.py:318-374``)."""
+        given = x
         if x is None:
             x = self.x
         else:
             x = validate_array(x, "x")
-        if self.x is not None and self.x is not x:
+        if self.x is not None and self.x is not x and self._x_given is not given:
             logger.warning(
                 "self.x has been set already, but is not equal to the argument x. "
                 "Current landmarks might be inapropriate."
