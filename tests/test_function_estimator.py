@@ -244,3 +244,20 @@ def test_predictor_with_observation_variance_round_trips_through_json(be, wave):
     assert rel(clone(X[:7]), est.predict(X[:7])) < 1e-12
     assert rel(clone.obs_variance(X[:7]), est.predict.obs_variance(X[:7])) < 1e-12
     assert rel(clone.leverage(X[:7]), est.predict.leverage(X[:7])) < 1e-12
+
+
+def test_same_x_rule_follows_the_object_the_caller_passed(be, wave):
+    """``set_x`` (base_model.py:176-213): passing the array the estimator was fitted on is fine, another one is an error —
+    also when validation had to copy it (an ndarray subclass here; a jax array for the reference's own tests)."""
+    X, y, _, _ = wave
+
+    class Tagged(np.ndarray):
+        pass
+
+    Xs = X.view(Tagged)
+    est = mb.FunctionEstimator(sigma=1e-2, ls=1.0)
+    first = est.fit_predict(Xs, y)
+    assert type(est.x) is np.ndarray or est.x is Xs
+    assert np.array_equal(est(Xs, y), first)                    # same object again: accepted
+    with pytest.raises(ValueError, match="has been set already"):
+        est.fit_predict(X.copy(), y)                            # equal values, different object: refused as in the reference
