@@ -102,6 +102,31 @@ def mle(nn_distances, d):
     return gammaln(d / 2 + 1) - (d / 2) * np.log(np.pi) - d * np.log(nn_distances)
 
 
+def distance_grad(x, eps=1e-12):
+    """``y -> (distance(x, y), d distance / d y)`` with shapes (n, m) and (n, m, d) (mellon/util.py:369-428).
+    The distances are the device kernel's; the gradient ``(y - x) / (distance + eps)`` is an element-wise host
+    expression over an array that is d times larger than anything on the path — a derivative utility like the
+    predictors' ``gradient``, not part of the accelerated path."""
+    x = ensure_2d(np.asarray(x, dtype=float))
+
+    def grad(y):
+        y = ensure_2d(np.asarray(y, dtype=float))
+        dist = np.asarray(distance(x, y))
+        if eps != 1e-12:                       # the kernel's constant is 1e-12 (util.py:365); re-base for another eps
+            dist = np.sqrt(np.maximum(dist * dist - 1e-12 + eps, 0))
+        delta = y[np.newaxis, :] - x[:, np.newaxis]
+        return dist, delta / (dist[..., np.newaxis] + eps)
+
+    return grad
+
+
+def set_jax_config(enable_x64=True, platform_name="cpu"):
+    """Kept for source compatibility (mellon/util.py:572-586): there is no JAX to configure.  Arithmetic is float64 on
+    the GPU whatever ``platform_name`` says; single precision is refused."""
+    if not enable_x64:
+        raise ValueError("mellon_b200 computes in float64 only.")
+
+
 def distance(x, y):
     """mellon/util.py:351-366 — sqrt(max(xx - 2xy + yy + 1e-12, 0)), evaluated by the same
     fused tile kernel as the covariances (leaf kind MB_K_DISTANCE)."""

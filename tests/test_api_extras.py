@@ -94,3 +94,22 @@ def test_per_cell_mean_in_transform_and_loss(be):
     np.testing.assert_allclose(grad, z + L.T @ (A - 1.0), rtol=1e-11, atol=1e-12 * scale)
     with pytest.raises(ValueError):
         mb.inference.compute_transform(mu[:-1], L)
+
+
+@pytest.mark.run_last
+def test_distance_grad_and_jax_config_shims(be):
+    """mellon/util.py:369-428, 572-586 (tests/test_util.py:22-56, 113-114 of the reference)."""
+    rng = np.random.default_rng(9)
+    x, y = rng.random((7, 3)), rng.random((5, 3))
+    dist, grad = mb.util.distance_grad(x)(y)
+    assert dist.shape == (7, 5) and grad.shape == (7, 5, 3)
+    np.testing.assert_allclose(dist, O.distance(x, y), rtol=1e-12)
+    h = 1e-6
+    for j in range(3):
+        e = np.zeros(3)
+        e[j] = h
+        fd = (O.distance(x, y + e) - O.distance(x, y - e)) / (2 * h)
+        np.testing.assert_allclose(grad[..., j], fd, atol=1e-6)
+    mb.util.set_jax_config()
+    with pytest.raises(ValueError):
+        mb.util.set_jax_config(enable_x64=False)
