@@ -30,7 +30,7 @@ def test_pack_writes_both_layouts_consistently():
     rng = np.random.default_rng(2)
     L = rng.standard_normal((40, 130))
     Ad, Bd, scale, nks = model.pack(L, 130)
-    assert nks == 2 and Ad.dtype == np.int8 and Ad.min() >= -64 and Ad.max() <= 63
+    assert nks == 2 and Ad.dtype == np.int8 and Ad.min() >= -model.HALF and Ad.max() <= model.HALF - 1
     # column 70 of A panel 0 is column 6 of B panel 1: same 16-byte pieces in both layouts, every slice and k-step
     for ks in range(nks):
         for t in range(model.NS):
@@ -42,7 +42,7 @@ def test_pack_writes_both_layouts_consistently():
     q = np.zeros(16, dtype=np.int64)
     for t in range(model.NS):
         a = t * model.ASLICE + 70 * 16
-        q += Ad[a:a + 16].astype(np.int64) * 128 ** (7 - t)
+        q += Ad[a:a + 16].astype(np.int64) * model.BASE ** (model.NS - 1 - t)
     np.testing.assert_allclose(q * scale[70], L[:16, 70], rtol=0, atol=2.0 ** -53 * np.max(np.abs(L[:, 70])))
 
 

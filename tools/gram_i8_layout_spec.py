@@ -9,7 +9,12 @@ import sys
 
 import numpy as np
 
-NS, KS, TA, TB = 8, 32, 128, 64
+import os
+
+DB = int(os.environ.get("DIGIT_BITS", 8))          # digit width of the build being modelled (-DDIGIT_BITS)
+NS, KS, TA, TB = (8 if DB == 7 else 7), 32, 128, 64
+HALF, BASE = 1 << (DB - 1), 1 << DB
+GROUPS = {7: [(0, 7), (1, 6), (2, 5), (3, 4)], 8: [(-1, 6), (0, 5), (1, 4), (2, 3)]}[DB]   # ISSUER_GROUPS, four warps
 ASLICE, BSLICE = 2 * TA * 16, 2 * TB * 16
 ABLOCK, BBLOCK = NS * ASLICE, NS * BSLICE
 
@@ -40,8 +45,8 @@ def pack(L, r):
                     if j < r and i < rows:
                         q = int(np.rint(np.ldexp(L[i, j], 54 - E)))
                     for t in range(NS - 1, -1, -1):
-                        d = ((q + 64) & 127) - 64
-                        q = (q - d) >> 7
+                        d = ((q + HALF) & (BASE - 1)) - HALF
+                        q = (q - d) >> DB
                         Ad[ab + t * ASLICE + chunk * (TA * 16) + col * 16 + c] = d
                         Bd[bb + t * BSLICE + chunk * (TB * 16) + (col & 63) * 16 + c] = d
     return Ad, Bd, scale, nks
@@ -67,8 +72,8 @@ def gram(L, r):
             tmem = np.zeros((128, 512), dtype=np.int64)
             for ks in range(nks):
                 sa, sb = (pa * nks + ks) * ABLOCK, (pb * nks + ks) * BBLOCK       # what the two bulk copies bring
-                for w in range(4):
-                    for g in (7 - w, w):
+                for g0, g1 in GROUPS:
+                    for g in (g1, g0):
                         for t in range(g + 1):
                             A = operand(Ad, sa + t * ASLICE, TA * 16, 128, TA)
                             B = operand(Bd, sb + (g - t) * BSLICE, TB * 16, 128, TB)
@@ -78,14 +83,14 @@ def gram(L, r):
                 gi = pa * TA + row
                 if gi >= r:
                     continue
-                si = scale[gi] * 2.0 ** 49
+                si = scale[gi] * 2.0 ** (DB * (NS - 1))
                 for c in range(TB):
                     gj = pb * TB + c
                     if gj >= r:
                         continue
                     h = 0.0
                     for g in range(NS):
-                        h = float(tmem[row, g * TB + c]) if g == 0 else h * 128.0 + float(tmem[row, g * TB + c])
+                        h = float(tmem[row, g * TB + c]) if g == 0 else h * float(BASE) + float(tmem[row, g * TB + c])
                     G[gi, gj] += h * si * scale[gj]
     return G
 
@@ -109,8 +114,8 @@ def pack_rows(X, expo, P, ks_lo, ks_hi, nks, Xd, scale):
                     if i < rows and k < cols:
                         q = int(np.rint(np.ldexp(X[i, k], 54 - E)))
                     for t in range(NS - 1, -1, -1):
-                        d = ((q + 64) & 127) - 64
-                        q = (q - d) >> 7
+                        d = ((q + HALF) & (BASE - 1)) - HALF
+                        q = (q - d) >> DB
                         Xd[blk + t * (2 * P * 16) + chunk * (P * 16) + row * 16 + c] = d
 
 
@@ -119,8 +124,8 @@ def gemm_tile(Ad, Bd, scale_a, scale_b, nks, a_stride, b_stride, pa, pb, rows_a,
     tmem = np.zeros((128, 512), dtype=np.int64)
     for ks in range(nks):
         sa, sb = (pa * a_stride + ks) * ABLOCK, (pb * b_stride + ks) * BBLOCK
-        for w in range(4):
-            for g in (7 - w, w):
+        for g0, g1 in GROUPS:
+            for g in (g1, g0):
                 for t in range(g + 1):
                     A = operand(Ad, sa + t * ASLICE, TA * 16, 128, TA)
                     B = operand(Bd, sb + (g - t) * BSLICE, TB * 16, 128, TB)
@@ -130,14 +135,14 @@ def gemm_tile(Ad, Bd, scale_a, scale_b, nks, a_stride, b_stride, pa, pb, rows_a,
         gi = pa * TA + row
         if gi >= rows_a:
             continue
-        si = alpha * scale_a[gi] * 2.0 ** 49
+        si = alpha * scale_a[gi] * 2.0 ** (DB * (NS - 1))
         for c in range(TB):
             gj = pb * TB + c
             if gj >= rows_b:
                 continue
             h = 0.0
             for g in range(NS):
-                h = float(tmem[row, g * TB + c]) if g == 0 else h * 128.0 + float(tmem[row, g * TB + c])
+                h = float(tmem[row, g * TB + c]) if g == 0 else h * float(BASE) + float(tmem[row, g * TB + c])
             out[gi, gj] += h * si * scale_b[gj]
 
 

@@ -6,12 +6,13 @@
 // by tools/microbench_umma_i8.cu and tools/k1_i8_proto_v2.cu.
 //
 // Scheme.  Contraction over the cells, so every COLUMN j of L gets one power-of-two scale 2^E_j (|L_ij| < 2^E_j over
-// the cell chunk) and each entry becomes a 54-bit fixed-point integer q = rint(L_ij 2^(54 - E_j)), written as 8
-// balanced base-128 digits d_0 (most significant) .. d_7 in [-64, 63].  A float64 product is the 36 int8 products
-// d_t d_u with t + u <= 7 (the dropped pairs are below 2^-56 of the scale product); products with equal g = t + u
-// share one int32 accumulator, so a 128 x 64 output tile keeps 8 accumulators of 64 TMEM columns = all 512 columns,
-// resident over a whole cell chunk.  |G_g| <= 8 * 4096 * KC, so the accumulators are flushed every KC = 32768 cells:
-// the flush folds H = sum_g G_g 128^(7-g) in float64 (Horner), scales by 2^(E_i + E_j - 108 + 49) and adds into G.
+// the cell chunk) and each entry becomes a 54-bit fixed-point integer q = rint(L_ij 2^(54 - E_j)), written as balanced
+// digits d_0 (most significant) .. d_(NS-1): by default NS = 7 digits of 8 bits in [-128, 127] (-DDIGIT_BITS=7: 8 digits
+// in [-64, 63]).  A float64 product is the int8 products d_t d_u with t + u <= NS - 1 (28, or 36; the dropped pairs are
+// below 2^-56 of the scale product); products with equal g = t + u share one int32 accumulator, so a 128 x 64 output
+// tile keeps NS accumulators of 64 TMEM columns (448 or all 512 columns), resident over a whole cell chunk.  |G_g| stays
+// below 2^31 for KC = 16384 (32768) cells, so the accumulators are flushed once per chunk: the flush folds
+// H = sum_g G_g B^(NS-1-g), B = 2^DIGIT_BITS, in float64 (Horner), scales by B^(NS-1) 2^(E_i + E_j - 108) and adds into G.
 //
 // Data flow per cell chunk (one pack launch + one GEMM launch, operands 2 x 1.3 GB of scratch at r = 5000):
 //   pack_kernel   L chunk (float64, row-major) -> digits, TRANSPOSED to K-major, in two tile-contiguous layouts
@@ -22,11 +23,11 @@
 //                 (each owns one or two digit-pair groups, at most 8 MMAs of 128 x 64 x 32 per k-step; ONE issuing thread sustains
 //                 only one MMA per ~144 clk whichever accumulator it targets, the rates of several issuing warps add up:
 //                 profiles/microbench_umma_i8_r01.txt), then the same four warps flush (tcgen05.ld lane quadrant = warp % 4).
-// Budget at r = 5000, N = 1e6: 1640 tiles x 31250 k-steps x 36 MMAs x 32 clk (full int8 rate) = 0.20 s on 148 SMs,
-// 0.30 s at the 5446 MAC/clk/SM measured for N = 64 tiles, against 0.85 s for the float64 DMMA SYRK; operand traffic
-// 48 KB per k-step = 28 B/clk/SM from L2.
+// Budget at r = 5000, N = 1e6 (8-bit digits): 1640 tiles x 31250 k-steps x 1008 clk (7 MMAs per issuing thread at one per
+// 144 clk; 896 clk at the full int8 rate) = 0.18 s on 148 SMs, against 0.85 s for the float64 DMMA SYRK; operand traffic
+// 42 KB per k-step = 42 B/clk/SM from L2 (7-bit digits: 48 KB per 1152-1296 clk).
 //
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo [-DISSUERS=4] -o gram_i8_proto gram_i8_proto.cu
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo [-DDIGIT_BITS=7 [-DISSUERS=4]] -o gram_i8_proto gram_i8_proto.cu
 // Run:   timeout 120 ./gram_i8_proto [N=65536] [R=640]          Gram matrix, checked against a long-double host reference
 //        timeout 120 ./gram_i8_proto trsm [N=8192] [M=640]     X <- X Lp^-T (K3, 37 % of a step) with the same GEMM kernel:
 //                                                              left-looking over 128-column blocks, digits of X packed as
@@ -42,25 +43,36 @@
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
 
-constexpr int NS = 8;                          // digit slices per value
+#ifndef DIGIT_BITS
+#define DIGIT_BITS 8
+#endif
+// Balanced digits of DIGIT_BITS bits.  8 (default): 7 digits in [-128, 127], the 28 pairs t + u <= 6, 7 group accumulators,
+// flush every 16384 cells — 22 % fewer MMAs than 7-bit digits (8 digits in [-64, 63], 36 pairs, 8 groups, flush every
+// 32768) for the same accuracy (profiles/ozaki_gemm_spec_r01.txt: 7.7e-17 against 8.9e-17 of |A||B|^T on the product alone).
+constexpr int DB = DIGIT_BITS;
+static_assert(DB == 7 || DB == 8, "digit width 7 or 8 bits");
+constexpr int NS = (DB == 7) ? 8 : 7;          // digit slices per value: 54-bit fixed point in either case
+constexpr long long DHALF = 1LL << (DB - 1), DMASK = (1LL << DB) - 1;
 constexpr int KS = 32;                         // cells per k-step (one kind::i8 MMA: K = 32)
 constexpr int TA = 128, TB = 64;               // output tile: 128 rows (A panel) x 64 columns (B panel)
 constexpr int ASLICE = 2 * TA * 16, ABLOCK = NS * ASLICE;   // 4 KB per slice, 32 KB per (A panel, k-step)
 constexpr int BSLICE = 2 * TB * 16, BBLOCK = NS * BSLICE;   // 2 KB per slice, 16 KB per (B panel, k-step)
 constexpr int NST = 4;                         // operand stages in flight
 #ifndef ISSUERS
-#define ISSUERS 5
+#define ISSUERS (DIGIT_BITS == 8 ? 4 : 5)
 #endif
-constexpr int NISS = ISSUERS;                  // MMA-issuing warps (4 or 5; build with -DISSUERS=4 to compare)
+constexpr int NISS = ISSUERS;                  // MMA-issuing warps (4 or 5)
 // digit-pair groups per issuing warp (a group g has g + 1 MMAs per k-step).  One thread issues one MMA per ~144 clk:
-//   4 warps: {0,7} {1,6} {2,5} {3,4} -> 9 MMAs each, 1296 clk per k-step;
-//   5 warps: {7} {6} {5,0} {4,1} {3,2} -> at most 8 each, 1152 clk = the k-step's 36 MMAs at the full int8 rate
-__device__ const int8_t ISSUER_GROUPS[2][5][2] = {{{0, 7}, {1, 6}, {2, 5}, {3, 4}, {-1, -1}},
-                                                 {{-1, 7}, {-1, 6}, {0, 5}, {1, 4}, {2, 3}}};
+//   8-bit digits, 4 warps: {6} {0,5} {1,4} {2,3} -> 7 MMAs each, 1008 clk per k-step (its 28 MMAs at the full int8 rate: 896 clk);
+//   7-bit digits, 4 warps: {0,7} {1,6} {2,5} {3,4} -> 9 each, 1296 clk; 5 warps: {7} {6} {0,5} {1,4} {2,3} -> at most 8, 1152 clk
+//   = the k-step's 36 MMAs at the full rate.  Rows: [digit width 7 / 8][4 / 5 warps].
+__device__ const int8_t ISSUER_GROUPS[2][2][5][2] = {
+    {{{0, 7}, {1, 6}, {2, 5}, {3, 4}, {-1, -1}}, {{-1, 7}, {-1, 6}, {0, 5}, {1, 4}, {2, 3}}},
+    {{{-1, 6}, {0, 5}, {1, 4}, {2, 3}, {-1, -1}}, {{-1, 6}, {-1, 5}, {0, 4}, {1, 3}, {-1, 2}}}};
 static_assert(NISS == 4 || NISS == 5, "group tables exist for 4 and 5 issuing warps");
 constexpr int NT = (1 + NISS) * 32;            // producer warp + issuer / flush warps
 constexpr int SMEM_TOTAL = NST * (ABLOCK + BBLOCK);         // 192 KB
-constexpr int KC = 32768;                      // cells per chunk: int32 accumulators hold 8 * 4096 * 32768 = 2^30
+constexpr int KC = (DB == 7) ? 32768 : 16384;  // cells per chunk: |G_g| <= NS * 2^(2 DB - 2) * KC = 2^30 (7 bits) / 7 * 2^28 (8 bits) < 2^31
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -99,8 +111,8 @@ pack_kernel(const double* __restrict__ L, int64_t rows, int64_t r, int64_t ld, c
     if (j < r && i < rows) q = llrint(ldexp(L[i * ld + j], 54 - E));
 #pragma unroll
     for (int t = NS - 1; t >= 0; t--) {
-      const long long d = ((q + 64) & 127) - 64;             // balanced digit in [-64, 63]
-      q = (q - d) >> 7;
+      const long long d = ((q + DHALF) & DMASK) - DHALF;     // balanced digit in [-2^(DB-1), 2^(DB-1) - 1]
+      q = (q - d) >> DB;
       dig[t][c >> 2] |= (uint32_t)(uint8_t)(int8_t)d << (8 * (c & 3));
     }
   }
@@ -143,8 +155,8 @@ pack_rows_kernel(const double* __restrict__ X, int64_t rows, int64_t cols, int64
     if (i < rows && k < cols) q = llrint(ldexp(X[i * ld + k], 54 - E));
 #pragma unroll
     for (int t = NS - 1; t >= 0; t--) {
-      const long long d = ((q + 64) & 127) - 64;
-      q = (q - d) >> 7;
+      const long long d = ((q + DHALF) & DMASK) - DHALF;
+      q = (q - d) >> DB;
       dig[t][c >> 2] |= (uint32_t)(uint8_t)(int8_t)d << (8 * (c & 3));
     }
   }
@@ -262,7 +274,7 @@ gram_i8_kernel(const int8_t* __restrict__ Ad, const int8_t* __restrict__ Bd, con
     }
   } else {
     // ---- issuers: warp 1 + w owns the digit-pair groups ISSUER_GROUPS[..][w] (g0 may be absent), accumulators at columns 64 g ----
-    const int w = warp - 1, g0 = ISSUER_GROUPS[NISS - 4][w][0], g1 = ISSUER_GROUPS[NISS - 4][w][1];
+    const int w = warp - 1, g0 = ISSUER_GROUPS[DB - 7][NISS - 4][w][0], g1 = ISSUER_GROUPS[DB - 7][NISS - 4][w][1];
     bool ok = true;
     if (lane == 0) {
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TB >> 3) << 17) | ((uint32_t)(TA >> 4) << 24);
@@ -299,7 +311,8 @@ gram_i8_kernel(const int8_t* __restrict__ Ad, const int8_t* __restrict__ Bd, con
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const int quad = warp & 3, row = quad * 32 + lane;
       const int64_t gi = (int64_t)pa * TA + row;
-      const double si = (gi < rows_a) ? alpha * scale_a[gi] * 0x1p49 : 0.0;   // 128^7 of the Horner form folded into the row scale
+      // Horner gives H = sum_g G_g B^(NS-1-g), B = 2^DB; the product is H B^(NS-1) 2^(E_i + E_j - 108): B^(NS-1) goes into the row scale
+      const double si = (gi < rows_a) ? alpha * scale_a[gi] * (double)(1LL << (DB * (NS - 1))) : 0.0;
       for (int c0 = 0; c0 < TB; c0 += 16) {
         double h[16];
 #pragma unroll
@@ -308,7 +321,7 @@ gram_i8_kernel(const int8_t* __restrict__ Ad, const int8_t* __restrict__ Bd, con
           tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * TB + c0), v);
           asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-          for (int e = 0; e < 16; e++) h[e] = (g == 0) ? (double)v[e] : fma(h[e], 128.0, (double)v[e]);
+          for (int e = 0; e < 16; e++) h[e] = (g == 0) ? (double)v[e] : fma(h[e], (double)(1 << DB), (double)v[e]);
         }
         if (gi < rows_a) {
 #pragma unroll
@@ -474,7 +487,7 @@ int main(int argc, char** argv) {
   }
   printf("status %s; max |G - G_ref| / (|L|^T |L|) = %.3e over %ld sampled lower entries (%ld above 1e-14)\n",
          st ? "TIMEOUT in an mbarrier wait" : "ok", worst, checked, bad);
-  const double macs = 36.0 * (double)htiles.size() * TA * TB * (double)n;
+  const double macs = (NS * (NS + 1) / 2) * (double)htiles.size() * TA * TB * (double)n;
   printf("pack %.3f ms, gemm %.3f ms: %.0f int8 MAC/clk/SM at 1.965 GHz x 148 SMs; float64-equivalent %.1f TF/s (2 N R^2 / 2 over gemm + pack)\n",
          ms_pack, ms_gemm, macs / (ms_gemm * 1e-3) / (148 * 1.965e9), (double)n * r * r / ((ms_gemm + ms_pack) * 1e-3) * 1e-12);
   printf("scaled to N=1e6, R=5000: gemm %.0f ms, pack %.0f ms (float64 DMMA SYRK today: ~850 ms)\n",

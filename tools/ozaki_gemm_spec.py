@@ -22,10 +22,12 @@ import scipy.linalg as sla
 
 from oracle import mellon_oracle as O
 
-NDIG = int(os.environ.get("OZ_DIGITS", 8))            # 7-bit balanced digits per value
+DBITS = int(os.environ.get("OZ_DIGIT_BITS", 7))       # bits per balanced digit: 7 (digits in [-64, 63]) or 8 ([-128, 127], the full int8 range)
+NDIG = int(os.environ.get("OZ_DIGITS", 8))            # digits per value
 ORDER = int(os.environ.get("OZ_ORDER", NDIG - 1))     # digit pairs kept: t + u <= ORDER
-BITS = 7 * NDIG - 2                                   # |q| <= 2^BITS fits NDIG balanced digits (8 digits: 54 bits)
-KCHUNK = 32768                                        # int32 accumulators: 8 pairs * 4096 * 32768 = 2^30 < 2^31
+BITS = DBITS * NDIG - 2                               # |q| <= 2^BITS fits NDIG balanced digits (8 x 7 bits: 54; 7 x 8 bits: 54)
+BASE, HALF = 1 << DBITS, 1 << (DBITS - 1)
+KCHUNK = 32768 if DBITS == 7 else 16384               # int32 accumulators: 8 pairs * 2^12 * 32768 = 2^30; 7 pairs * 2^14 * 16384 < 2^31
 
 
 def pack_rows(v):
@@ -36,9 +38,9 @@ def pack_rows(v):
     digits = np.empty((NDIG,) + v.shape, dtype=np.int8)
     rem = q
     for t in range(NDIG - 1, -1, -1):
-        d = ((rem + 64) % 128) - 64
+        d = ((rem + HALF) % BASE) - HALF
         digits[t] = d
-        rem = (rem - d) // 128
+        rem = (rem - d) // BASE
     assert np.all(rem == 0)
     return digits, E
 
@@ -58,10 +60,10 @@ def ozaki_nt(A, B):
         for g in range(ORDER + 1):
             G = None
             for t in range(max(0, g - NDIG + 1), min(g, NDIG - 1) + 1):
-                P = fa[t] @ fb[g - t]                    # exact: |sum| <= 4096 * KCHUNK = 2^27
+                P = fa[t] @ fb[g - t]                    # exact: |sum| <= HALF^2 * KCHUNK <= 2^28
                 G = P if G is None else G + P            # exact integer group sum (int32 on the device)
-            S = G if S is None else S * 128.0 + G        # Horner in float64 (the device folds two groups on the integer pipe first: same value)
-        out += S * np.ldexp(1.0, 7 * (2 * (NDIG - 1) - ORDER))
+            S = G if S is None else S * float(BASE) + G  # Horner in float64 (the device folds two groups on the integer pipe first: same value)
+        out += S * np.ldexp(1.0, DBITS * (2 * (NDIG - 1) - ORDER))
     return out * np.ldexp(1.0, EA - BITS)[:, None] * np.ldexp(1.0, EB - BITS)[None, :]
 
 
@@ -114,7 +116,7 @@ if __name__ == "__main__":
     X = np.random.default_rng(0).random((n, 50))
     lm = np.ascontiguousarray(X[np.sort(np.random.default_rng(1).choice(n, m, replace=False))])
     nn = O.compute_nn_distances(X)
-    print(f"config 2 in small: ExpQuad, N = {n}, M = {m}, D = 50, ls = {O.compute_ls(nn):.2f}; {NDIG} digits, pairs t + u <= {ORDER} "
+    print(f"config 2 in small: ExpQuad, N = {n}, M = {m}, D = 50, ls = {O.compute_ls(nn):.2f}; {NDIG} digits of {DBITS} bits, pairs t + u <= {ORDER} "
           f"({sum(1 for t in range(NDIG) for u in range(NDIG) if t + u <= ORDER)} int8 products per float64 product)", flush=True)
 
     # the product alone, against an 80-bit reference, on the two operand shapes
