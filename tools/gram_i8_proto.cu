@@ -27,6 +27,10 @@
 // 144 clk; 896 clk at the full int8 rate) = 0.18 s on 148 SMs, against 0.85 s for the float64 DMMA SYRK; operand traffic
 // 42 KB per k-step = 42 B/clk/SM from L2 (7-bit digits: 48 KB per 1152-1296 clk).
 //
+// If the mode-1 run (operand ring only) shows the copies, not the MMAs, bound the kernel (42 B/clk/SM is 12 TB/s of L2
+// reads chip-wide), the next step is a cluster of 2 or 4 CTAs with the same A panel and neighbouring B panels that
+// multicasts the A block (28 KB -> 14 / 7 KB per CTA and k-step: 28 / 21 B/clk/SM).
+//
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo [-DDIGIT_BITS=7 [-DISSUERS=4]] -o gram_i8_proto gram_i8_proto.cu
 // Run:   timeout 120 ./gram_i8_proto [N=65536] [R=640]          Gram matrix, checked against a long-double host reference
 //        timeout 120 ./gram_i8_proto trsm [N=8192] [M=640]     X <- X Lp^-T (K3, 37 % of a step) with the same GEMM kernel:
