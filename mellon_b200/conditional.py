@@ -434,29 +434,29 @@ class _LandmarksConditional:
             raise ValueError("Unsupported sigma configuration.")
         G = be.gram(At)
         self._At, self._G, self._Lp = At, G, Lp           # scratch of __init__, dropped below
-
-        if per_feature:
-            cols = _sigma_columns(sigma)
-            weights = np.stack([self._sparse_solve(r[:, g], _inverse_variance(s))[0] for g, s in enumerate(cols)], axis=1)
-            L_B = None
-        else:
-            scale = 1.0
-            if not y_is_mean:
-                scale = self._noise_scale(sigma, r)
-            weights, L_B = self._sparse_solve(r, scale)
-
-        self.cov_func = cov_func
-        self.landmarks = _host(xu)
-        self.weights = weights
-        self.mu = mu
-        self.jitter = jitter
-        self.sigma = original_sigma
-        self.per_feature_sigma = per_feature
-        self.n_input_features = xu.shape[1]
-        self.n_obs = x.shape[0]
-        self._state_variables = {"landmarks", "weights", "mu", "jitter", "sigma", "per_feature_sigma"}
-
         try:
+            if per_feature:
+                cols = _sigma_columns(sigma)
+                weights = np.stack([self._sparse_solve(r[:, g], _inverse_variance(s))[0]
+                                    for g, s in enumerate(cols)], axis=1)
+                L_B = None
+            else:
+                scale = 1.0
+                if not y_is_mean:
+                    scale = self._noise_scale(sigma, r)
+                weights, L_B = self._sparse_solve(r, scale)
+
+            self.cov_func = cov_func
+            self.landmarks = _host(xu)
+            self.weights = weights
+            self.mu = mu
+            self.jitter = jitter
+            self.sigma = original_sigma
+            self.per_feature_sigma = per_feature
+            self.n_input_features = xu.shape[1]
+            self.n_obs = x.shape[0]
+            self._state_variables = {"landmarks", "weights", "mu", "jitter", "sigma", "per_feature_sigma"}
+
             if obs_variance:
                 self._compute_obs_variance(x, y, sigma)
             if not with_uncertainty:
