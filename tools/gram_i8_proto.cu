@@ -78,7 +78,32 @@ constexpr int NT = (1 + NISS) * 32;            // producer warp + issuer / flush
 constexpr int SMEM_TOTAL = NST * (ABLOCK + BBLOCK);         // 192 KB
 constexpr int KC = (DB == 7) ? 32768 : 16384;  // cells per chunk: |G_g| <= NS * 2^(2 DB - 2) * KC = 2^30 (7 bits) / 7 * 2^28 (8 bits) < 2^31
 
+#ifndef CLUSTER
+#define CLUSTER 1
+#endif
+// -DCLUSTER=2: the two CTAs of a cluster work on the same A panel and neighbouring B panels; each fetches HALF of the A
+// block of a k-step and multicasts it into both CTAs' shared memory (cp.async.bulk ... .multicast::cluster), so the A
+// traffic per CTA halves (42 -> 28 KB per k-step with 8-bit digits).  A stage may be refilled only when BOTH CTAs are
+// done with it: after its own `empty` wait each producer signals the peer's `peer_ready` barrier (remote mbarrier
+// arrive) and waits for the peer's signal on its own.  Default 1 (off): the plain kernel is the one to validate first.
+constexpr int CL = CLUSTER;
+static_assert(CL == 1 || CL == 2, "cluster size 1 or 2");
+
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+               "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(s_u32(bar)), "r"(rank) : "memory");
+}
+// bulk copy into the same offset of every CTA in `mask`; each destination CTA's barrier receives the bytes
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n" ::"r"(
+                   s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)), "h"(mask) : "memory");
+}
 
 // ---- column scales: max |L_ij| over the chunk, as the bit pattern of a non-negative double (ordered like uint64) ------
 __global__ void colmax_kernel(const double* __restrict__ L, int64_t rows, int64_t r, int64_t ld,
@@ -241,15 +266,16 @@ __global__ void __launch_bounds__(NT, 1)
 gram_i8_kernel(const int8_t* __restrict__ Ad, const int8_t* __restrict__ Bd, const double* __restrict__ scale_a,
                const double* __restrict__ scale_b, int64_t nks, int64_t a_stride_ks, int64_t b_stride_ks,
                const int2* __restrict__ tiles, int64_t rows_a, int64_t rows_b,
-               double alpha, double* __restrict__ G, int64_t ldg, int* __restrict__ status, int mode = 0) {
+               double alpha, double* __restrict__ G, int64_t ldg, int* __restrict__ status, int mode) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t full[NST], empty[NST], done;
+  __shared__ __align__(8) uint64_t full[NST], empty[NST], peer_ready[NST], done;
   __shared__ uint32_t tmem_base_sh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int pa = tiles[blockIdx.x].x, pb = tiles[blockIdx.x].y;
+  const int pa = tiles[blockIdx.x].x, pb = tiles[blockIdx.x].y;       // CLUSTER=2: the pair (2i, 2i+1) shares pa
+  const uint32_t crank = (CL > 1) ? cluster_rank() : 0u;
 
   if (tid == 0) {
-    for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NISS); }
+    for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NISS); mbar_init(&peer_ready[s], 1); }
     mbar_init(&done, NISS);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -259,6 +285,7 @@ gram_i8_kernel(const int8_t* __restrict__ Ad, const int8_t* __restrict__ Bd, con
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  if (CL > 1) cluster_sync_all();          // the peer's barriers exist before anything is sent to them
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = tmem_base_sh;
 
@@ -271,6 +298,15 @@ gram_i8_kernel(const int8_t* __restrict__ Ad, const int8_t* __restrict__ Bd, con
         const int s = (int)(ks % NST);
         if (ks >= NST && !mbar_wait(&empty[s], (uint32_t)(((ks / NST) - 1) & 1), status)) break;
         unsigned char* stage = smem + s * (ABLOCK + BBLOCK);
+        if (CL > 1) {
+          // my stage s is free: tell the peer, and wait until the peer's stage s is free too (its signal, k-th use -> parity)
+          mbar_arrive_remote(&peer_ready[s], crank ^ 1u);
+          if (!mbar_wait(&peer_ready[s], (uint32_t)((ks / NST) & 1), status)) break;
+          mbar_expect_tx(&full[s], ABLOCK + BBLOCK);          // both halves of A (one from each CTA) + my B block
+          bulk_g2s_multicast(stage + crank * (ABLOCK / 2), asrc + ks * ABLOCK + crank * (ABLOCK / 2), ABLOCK / 2, &full[s], 3);
+          bulk_g2s(stage + ABLOCK, bsrc + ks * BBLOCK, BBLOCK, &full[s]);
+          continue;
+        }
         mbar_expect_tx(&full[s], ABLOCK + BBLOCK);
         bulk_g2s(stage, asrc + ks * ABLOCK, ABLOCK, &full[s]);
         bulk_g2s(stage + ABLOCK, bsrc + ks * BBLOCK, BBLOCK, &full[s]);
@@ -339,7 +375,23 @@ gram_i8_kernel(const int8_t* __restrict__ Ad, const int8_t* __restrict__ Bd, con
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  if (CL > 1) cluster_sync_all();          // no CTA leaves while its peer may still write into it or signal it
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+// launch with the cluster dimension of the build (the tile list keeps the two tiles of a pair adjacent)
+template <typename... Args>
+static void launch_gemm(unsigned grid, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = SMEM_TOTAL;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, gram_i8_kernel, args...));
 }
 
 // ---- TRSM driver: X <- X Lp^-T, left-looking over 128-column blocks; every update X_j -= X[:, :j0] Lp[j, :j0]^T on int8 slices ----
@@ -408,7 +460,7 @@ static int run_trsm(int64_t n, int64_t m) {
       if (b > 0) {
         for (int64_t p = 0; p < npx; p++) { ht[2 * p] = make_int2((int)p, (int)(2 * b)); ht[2 * p + 1] = make_int2((int)p, (int)(2 * b + 1)); }
         CK(cudaMemcpyAsync(tiles, ht.data(), ht.size() * sizeof(int2), cudaMemcpyHostToDevice));
-        gram_i8_kernel<<<(unsigned)(2 * npx), NT, SMEM_TOTAL>>>(Xd, Lpd, sx, sl, j0 / KS, nks_total, nks_total, tiles, n, m, -1.0, X, m, status);
+        launch_gemm((unsigned)(2 * npx), (const int8_t*)Xd, (const int8_t*)Lpd, (const double*)sx, (const double*)sl, (int64_t)(j0 / KS), nks_total, nks_total, (const int2*)tiles, n, m, -1.0, X, m, status, 0);
         CK(cudaStreamSynchronize(0));                        // `ht` is reused by the next block (prototype: pageable copy)
       }
       diag_solve_kernel<<<(unsigned)n, 128>>>(X, n, m, j0, TA, Tinv + b * 128 * 128);
@@ -468,7 +520,7 @@ int main(int argc, char** argv) {
       colmax_kernel<<<dim3((unsigned)((r + 127) / 128), 64), 128>>>(L + c0 * r, rows, r, r, cmax);
       pack_kernel<<<dim3((unsigned)npa, (unsigned)nks), 256>>>(L + c0 * r, rows, r, r, cmax, nks, Ad, Bd, scale);
       CK(cudaEventRecord(b));
-      gram_i8_kernel<<<(unsigned)htiles.size(), NT, SMEM_TOTAL>>>(Ad, Bd, scale, scale, nks, nks, nks, tiles, r, r, 1.0, G, r, status);
+      launch_gemm((unsigned)htiles.size(), (const int8_t*)Ad, (const int8_t*)Bd, (const double*)scale, (const double*)scale, nks, nks, nks, (const int2*)tiles, r, r, 1.0, G, r, status, 0);
       CK(cudaEventRecord(c)); CK(cudaEventSynchronize(c));
       float x, y; CK(cudaEventElapsedTime(&x, a, b)); CK(cudaEventElapsedTime(&y, b, c)); tp += x; tg += y;
       CK(cudaEventDestroy(a)); CK(cudaEventDestroy(b)); CK(cudaEventDestroy(c));
@@ -500,7 +552,7 @@ int main(int argc, char** argv) {
     const int64_t rows = (n % KC) ? (n % KC) : (n < KC ? n : KC), nks = (rows + KS - 1) / KS;
     float ms = 0;
     CK(cudaEventRecord(e0));
-    gram_i8_kernel<<<(unsigned)htiles.size(), NT, SMEM_TOTAL>>>(Ad, Bd, scale, scale, nks, nks, nks, tiles, r, r, 1.0, G, r, status, 1);
+    launch_gemm((unsigned)htiles.size(), (const int8_t*)Ad, (const int8_t*)Bd, (const double*)scale, (const double*)scale, nks, nks, nks, (const int2*)tiles, r, r, 1.0, G, r, status, 1);
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
     printf("mode 1 (operand ring only, one chunk of %lld cells): %.3f ms = %.1f B/clk/SM\n", (long long)rows, ms,
            (double)htiles.size() * nks * (ABLOCK + BBLOCK) / (ms * 1e-3) / (148 * 1.965e9));

@@ -18,7 +18,7 @@ echo "gpu suite exit $?" >> "$OUT/pytest_gpu.txt"
 
 # 2. prototypes: Gram matrix and TRSM on tcgen05 int8 digit slices (small first: correctness; then a timing size)
 NVCC="nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo"
-(cd tools && $NVCC -o gram_i8_proto gram_i8_proto.cu && $NVCC -DDIGIT_BITS=7 -o gram_i8_proto7 gram_i8_proto.cu) > "$OUT/build.txt" 2>&1
+(cd tools && $NVCC -o gram_i8_proto gram_i8_proto.cu && $NVCC -DDIGIT_BITS=7 -o gram_i8_proto7 gram_i8_proto.cu && $NVCC -DCLUSTER=2 -o gram_i8_proto_c2 gram_i8_proto.cu) > "$OUT/build.txt" 2>&1
 for args in "4096 256" "65536 640" "131072 5000"; do
   echo "== gram $args" >> "$OUT/gram_i8_proto.txt"
   timeout 120 tools/gram_i8_proto $args >> "$OUT/gram_i8_proto.txt" 2>&1
@@ -27,6 +27,11 @@ done
 echo "== gram 65536 640, 7-bit digits (36 products, five issuing warps)" >> "$OUT/gram_i8_proto.txt"
 timeout 120 tools/gram_i8_proto7 65536 640 >> "$OUT/gram_i8_proto.txt" 2>&1
 echo "exit $?" >> "$OUT/gram_i8_proto.txt"
+for args in "4096 256" "131072 5000"; do     # only after the plain build is exact: A block multicast across a 2-CTA cluster
+  echo "== gram $args, CLUSTER=2" >> "$OUT/gram_i8_proto.txt"
+  timeout 120 tools/gram_i8_proto_c2 $args >> "$OUT/gram_i8_proto.txt" 2>&1
+  echo "exit $?" >> "$OUT/gram_i8_proto.txt"
+done
 for args in "1024 256" "8192 640" "131072 2560"; do
   echo "== trsm $args" >> "$OUT/gram_i8_proto.txt"
   timeout 180 tools/gram_i8_proto trsm $args >> "$OUT/gram_i8_proto.txt" 2>&1
