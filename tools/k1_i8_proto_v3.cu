@@ -106,6 +106,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* s
     if (!ok) {
       if (backoff_ns) __nanosleep(backoff_ns);
       if (++spins > 20000000LL) { atomicExch(status, 1); return; }
+      if ((spins & 1023) == 0 && *(volatile int*)status) return;   // some wait has timed out already: drain the grid quickly
     }
   }
 }
