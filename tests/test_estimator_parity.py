@@ -48,6 +48,7 @@ def blobs(n, d, seed, k=6, spread=0.25):
     return centers[rng.integers(0, k, n)] + spread * rng.standard_normal((n, d))
 
 
+@pytest.mark.run_last          # computes its nn_distances itself: on the device since the end of round 1
 def test_config1_readme_smoke_full_gp(be):
     """BASELINE configs[0]: DensityEstimator().fit_predict(rand(100, 10)), default Matern52 -> FULL GP."""
     X = np.random.default_rng(0).random((100, 10))
@@ -152,6 +153,7 @@ def test_full_nystroem(be, tight):
     assert rel(dens, ref.log_density_x) < TOL
 
 
+@pytest.mark.run_last          # computes its nn_distances itself: on the device since the end of round 1
 def test_one_dimensional_input_and_default_pipeline(be, tight):
     x = np.random.default_rng(3).standard_normal(400)
     est = mb.DensityEstimator()
@@ -161,6 +163,7 @@ def test_one_dimensional_input_and_default_pipeline(be, tight):
     assert rel(dens, ref.log_density_x) < TOL
 
 
+@pytest.mark.run_last          # computes its nn_distances itself: on the device since the end of round 1
 def test_default_landmarks_kmeans_identical_on_both_sides(be, tight):
     """With landmarks=None both sides call sklearn k_means(n_init=1, random_state=42)."""
     X = blobs(1200, 5, 12)
@@ -209,6 +212,7 @@ def test_laplace_uncertainty(be):
     np.testing.assert_allclose(pred.mean_covariance(Y), mvar, rtol=1e-4)
 
 
+@pytest.mark.run_last          # computes its nn_distances itself: on the device since the end of round 1
 def test_time_sensitive_estimator(be, tight):
     rng = np.random.default_rng(21)
     n_per, T, d = 300, 4, 3
@@ -238,6 +242,7 @@ def test_time_sensitive_estimator(be, tight):
     assert mt.shape == (50, 2) and np.allclose(mt[:, 0], at1, rtol=1e-13)
 
 
+@pytest.mark.run_last          # computes its nn_distances itself: on the device since the end of round 1
 def test_error_contracts(be):
     X = np.random.default_rng(0).random((60, 3))
     est = mb.DensityEstimator()
@@ -261,6 +266,7 @@ def test_error_contracts(be):
     assert np.allclose(p(X, normalize=True), p(X) - np.log(60))
 
 
+@pytest.mark.run_last          # computes its nn_distances itself: on the device since the end of round 1
 def test_predictor_json_roundtrip(be, tmp_path):
     X = blobs(500, 4, 40)
     est = mb.DensityEstimator(n_landmarks=40)

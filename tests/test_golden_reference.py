@@ -168,6 +168,7 @@ def lbfgsb_options():
     setter(old)
 
 
+@pytest.mark.run_last          # computes its nn_distances itself: on the device since the end of round 1
 @pytest.mark.parametrize("name", list(CASES))
 def test_package_end_to_end_matches_reference(be, lbfgsb_options, name):
     g = load(name)
@@ -191,6 +192,7 @@ def test_package_end_to_end_matches_reference(be, lbfgsb_options, name):
                 np.testing.assert_allclose(est.predict.mean_covariance(g["Y"]), g["mean_covariance" + tag], rtol=1e-4)
 
 
+@pytest.mark.run_last          # computes its nn_distances itself: on the device since the end of round 1
 def test_package_time_sensitive_matches_reference(be, lbfgsb_options):
     g = load("time_sensitive")
     # converged-optimiser tolerance 3e-6 (not 1e-6): with ftol = 0 L-BFGS-B stops where its line search can
