@@ -58,6 +58,7 @@ def test_predictor_derivatives_match_finite_differences_of_the_oracle(be):
         np.testing.assert_allclose(g, np.einsum("i,ijd->jd", w.reshape(-1), kg), rtol=1e-6, atol=1e-8)
 
 
+@pytest.mark.run_last          # computes its nn_distances itself: on the device since the end of round 1
 def test_time_predictor_derivatives_shapes(be):
     rng = np.random.default_rng(3)
     X = rng.standard_normal((160, 2)) * 0.5
