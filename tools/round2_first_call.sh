@@ -38,7 +38,7 @@ for args in "1024 256" "8192 640" "131072 2560"; do
   echo "exit $?" >> "$OUT/gram_i8_proto.txt"
 done
 
-# 2b. K1 on int8 slices, v3 (five issuing warps, drain-then-compute epilogue) next to v2 for the before / after
+# 2b. K1 on int8 slices, v3 (four issuing warps, drain-then-compute epilogue) next to v2 for the before / after
 (cd tools && $NVCC -o k1_i8_proto_v3 k1_i8_proto_v3.cu && $NVCC -o k1_i8_proto_v2 k1_i8_proto_v2.cu) >> "$OUT/build.txt" 2>&1
 for exe in k1_i8_proto_v3 k1_i8_proto_v2; do
   echo "== $exe 131072 5120" >> "$OUT/k1_i8_proto.txt"
