@@ -261,3 +261,42 @@ def test_same_x_rule_follows_the_object_the_caller_passed(be, wave):
     assert np.allclose(est(Xs, y), first, rtol=1e-10, atol=0)    # same object again: accepted
     with pytest.raises(ValueError, match="has been set already"):
         est.fit_predict(X.copy(), y)                            # equal values, different object: refused as in the reference
+
+
+def test_random_configurations_against_the_oracle(be):
+    """Shapes, noise forms (scalar / per-feature / per-observation / per-observation-per-feature), full and sparse,
+    with and without observation variance and covariance: the package against the oracle restatement."""
+    rng = np.random.default_rng(0)
+    tol = 1e-8 if type(be).__name__ == "FakeBackend" else 1e-6
+    for trial in range(24):
+        n, d, p = int(rng.integers(20, 90)), int(rng.integers(1, 5)), int(rng.integers(1, 4))
+        X, Xq = rng.standard_normal((n, d)), rng.standard_normal((7, d))
+        y = rng.standard_normal((n, p)) if rng.random() < 0.7 else rng.standard_normal(n)
+        sparse = rng.random() < 0.5
+        lm = X[rng.choice(n, int(rng.integers(3, min(15, n - 1))), replace=False)].copy() if sparse else None
+        form = rng.choice(["scalar", "pf", "obs", "np"])
+        if form == "pf" and y.ndim == 2:
+            sigma = rng.random(y.shape[1]) + 0.2
+        elif form == "obs" and y.ndim == 1:
+            sigma = rng.random(n) + 0.2
+        elif form == "np" and y.ndim == 2:
+            sigma = rng.random(y.shape) + 0.2
+        else:
+            sigma, form = float(rng.random() + 0.2), "scalar"
+        obs = form in ("scalar", "pf") and rng.random() < 0.6
+        unc = rng.random() < 0.5
+        ls, mu = float(rng.random() * 2 + 0.5), float(rng.standard_normal())
+        est = mb.FunctionEstimator(landmarks=lm, n_landmarks=None if sparse else 0, ls=ls, mu=mu, sigma=sigma,
+                                   obs_variance=obs, predictor_with_uncertainty=unc).fit(X, y)
+        fit = O.function_fit(X, y, landmarks=lm, mu=mu, cov_func=O.Matern52(ls), sigma=sigma, obs_variance=obs,
+                             with_uncertainty=unc)
+        case = (trial, n, d, p, sparse, form, obs, unc)
+        assert rel(est.predict.weights, fit.weights) < tol, case
+        assert rel(est.predict(Xq), O.conditional_mean(Xq, fit.base, fit.weights, mu, fit.cov_func)) < tol, case
+        if form in ("scalar", "pf"):
+            assert rel(est.predict.leverage(Xq), O.function_leverage(fit, Xq)) < tol, case
+        if obs:
+            assert rel(est.predict.obs_variance(Xq), O.function_obs_variance(fit, Xq)) < tol, case
+        if unc:
+            nf = dict(noise_free=True) if est.predict.per_feature_sigma else {}
+            assert rel(est.predict.covariance(Xq, **nf), O.function_covariance(fit, Xq)) < tol, case
