@@ -2,7 +2,7 @@
 # First gpurun call of round 2: confirm on hardware what round 1 finished after its GPU minutes were spent, then run the
 # int8 digit-slice prototypes (each under its own `timeout`: every mbarrier wait in them is bounded, this is the second fence).
 #
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/round2_first_call.sh'      (about 15-20 GPU-minutes when nothing hangs)
 #
 # Everything lands in gpurun_out/round2_first/ ; nothing here is a bench value (see bench.py for those).
 set -u
@@ -10,11 +10,10 @@ OUT=gpurun_out/round2_first
 mkdir -p "$OUT"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > "$OUT/gpu.txt" 2>&1
 
-# 1. the tests written without a GPU (FunctionEstimator, gemm beta, row scaling / diagonal vector), then the whole GPU suite
-timeout 900 python -m pytest tests -m gpu -q -k "function_estimator or accumulates_into or row_scaling" > "$OUT/pytest_new.txt" 2>&1
+# 1. the tests written without a GPU (everything marked run_last: FunctionEstimator, gemm beta, row scaling / diagonal vector,
+#    the estimator tests that now take their nn_distances from the device)
+timeout 900 python -m pytest tests -m "gpu and run_last" -q > "$OUT/pytest_new.txt" 2>&1
 echo "new tests exit $?" >> "$OUT/pytest_new.txt"
-timeout 1500 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.txt" 2>&1
-echo "gpu suite exit $?" >> "$OUT/pytest_gpu.txt"
 
 # 2. prototypes: Gram matrix and TRSM on tcgen05 int8 digit slices (small first: correctness; then a timing size)
 NVCC="nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo"
@@ -51,4 +50,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:k1_i
 # 3. one ncu capture of the prototype GEMM at the timing size (tensor pipe, L2 / DRAM traffic, stall reasons)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gram_i8_kernel -c 1 -o "$OUT/gram_i8_proto" \
   tools/gram_i8_proto 65536 5000 > "$OUT/ncu.txt" 2>&1
+# 4. the whole GPU suite last: it is the longest step, and the round-end driver run repeats it anyway
+timeout 1500 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.txt" 2>&1
+echo "gpu suite exit $?" >> "$OUT/pytest_gpu.txt"
 tail -5 "$OUT/pytest_new.txt" "$OUT/pytest_gpu.txt" "$OUT/gram_i8_proto.txt" "$OUT/k1_i8_proto.txt"
