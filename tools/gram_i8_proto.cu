@@ -416,8 +416,8 @@ static int run_trsm(int64_t n, int64_t m) {
       hLp[(size_t)i * m + j] = t / piv;
     }
   }
-  srand(5);
-  for (auto& v : hC) v = rand() / (double)RAND_MAX - 0.3;
+  uint64_t rs = 0xD1B54A32D192ED03ull;
+  for (auto& v : hC) { rs ^= rs >> 12; rs ^= rs << 25; rs ^= rs >> 27; v = (double)((rs * 0x2545F4914F6CDD1Dull) >> 11) * 0x1p-53 - 0.3; }
   const int64_t nref = n < 1024 ? n : 1024;                                // rows solved on the host: the check, and the exponents
   for (int64_t i = 0; i < nref; i++) for (int64_t j = 0; j < m; j++) {     // host reference: forward substitution per row
     long double t = hC[(size_t)i * m + j];
@@ -490,12 +490,13 @@ int main(int argc, char** argv) {
   const int64_t npa = (r + TA - 1) / TA, npb = 2 * npa;
   printf("Gram int8-slice prototype: N=%lld R=%lld (%lld A panels), chunk %d cells\n", (long long)n, (long long)r, (long long)npa, KC);
   // L as the path produces it: a whitened covariance block — columns of very different magnitude, rows correlated
-  std::vector<double> hL((size_t)n * r);
-  srand(11);
+  std::vector<double> hL((size_t)n * r), colscale(r);
+  for (int64_t j = 0; j < r; j++) colscale[j] = pow(10.0, -6.0 * j / (double)r);
+  uint64_t rs = 0x9E3779B97F4A7C15ull;                       // xorshift64*: the host side must not eat GPU-box minutes
+  auto uni = [&rs]() { rs ^= rs >> 12; rs ^= rs << 25; rs ^= rs >> 27; return (double)((rs * 0x2545F4914F6CDD1Dull) >> 11) * 0x1p-53 - 0.5; };
   for (int64_t i = 0; i < n; i++) {
-    const double base = rand() / (double)RAND_MAX - 0.5;
-    for (int64_t j = 0; j < r; j++)
-      hL[(size_t)i * r + j] = (base + 0.3 * (rand() / (double)RAND_MAX - 0.5)) * pow(10.0, -6.0 * j / (double)r);
+    const double base = uni();
+    for (int64_t j = 0; j < r; j++) hL[(size_t)i * r + j] = (base + 0.3 * uni()) * colscale[j];
   }
   std::vector<int2> htiles;
   for (int pa = 0; pa < npa; pa++) for (int pb = 0; pb < npb; pb++) if (64 * pb < 128 * (pa + 1)) htiles.push_back(make_int2(pa, pb));
