@@ -47,6 +47,12 @@ cases = {
     "composite_cov": (lambda: mb.DensityEstimator(cov_func=(mb.cov.Matern32(1.1, active_dims=[0, 1]) + mb.cov.RatQuad(2.0, 0.9)) * 0.7 + 0.05,
                                                   landmarks=lmc), Xc, (), Yc, ()),
 }
+# regression predictors (FunctionEstimator): multi-output weights, per-feature sigma, observation-variance weights
+yc = np.stack([np.sin(Xc[:, 0]), Xc[:, 1] * Xc[:, 2]], axis=1)
+cases["function_sparse_obsvar"] = (lambda: mb.FunctionEstimator(landmarks=lmc, ls=1.5, sigma=np.array([0.3, 0.6]), obs_variance=True,
+                                                               predictor_with_uncertainty=True), Xc, (yc,), Yc, ())
+cases["function_full_obsvar"] = (lambda: mb.FunctionEstimator(n_landmarks=0, ls=1.5, sigma=0.4, obs_variance=True,
+                                                             predictor_with_uncertainty=True), Xc[:120], (yc[:120],), Yc, ())
 worst = 0.0
 for name, (make, X, fit_args, Y, pred_args) in cases.items():
     est = make()
@@ -54,8 +60,14 @@ for name, (make, X, fit_args, Y, pred_args) in cases.items():
     ours = est.predict
     theirs = mellon.Predictor.from_json_str(ours.to_json())
     assert type(theirs).__module__.startswith("mellon.") and type(theirs).__name__ == type(ours).__name__
-    checks = {"mean": (ours(Y, *pred_args), theirs(Y, *pred_args)),
-              "mean normalized": (ours(Y, *pred_args, normalize=True), theirs(Y, *pred_args, normalize=True))}
+    checks = {"mean": (ours(Y, *pred_args), theirs(Y, *pred_args))}
+    if name.startswith("function_"):
+        nf = dict(noise_free=True) if ours.per_feature_sigma else {}
+        checks["obs_variance"] = (ours.obs_variance(Y), theirs.obs_variance(Y))
+        checks["leverage"] = (ours.leverage(Y), theirs.leverage(Y))
+        checks["covariance"] = (ours.covariance(Y, **nf), theirs.covariance(Y, **nf))
+    else:
+        checks["mean normalized"] = (ours(Y, *pred_args, normalize=True), theirs(Y, *pred_args, normalize=True))
     if name == "sparse_cholesky_laplace":
         checks["covariance"] = (ours.covariance(Y), theirs.covariance(Y))
         checks["mean_covariance"] = (ours.mean_covariance(Y), theirs.mean_covariance(Y))
