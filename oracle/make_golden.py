@@ -154,6 +154,7 @@ def main():
 
     serialised_predictors()
     function_estimator()
+    serialised_function_predictors()
 
 
 def serialised_predictors():
@@ -258,8 +259,39 @@ def function_estimator():
     save("function_estimator", **out)
 
 
+def serialised_function_predictors():
+    """FunctionEstimator predictors fitted AND serialised by the reference, with its own numbers at a few query points:
+    tests/test_function_estimator.py loads the JSON text with this package (SURVEY.md §8f.3 + §8f.4)."""
+    import json
+
+    Xc, Yc = blobs(300, 4, 41), blobs(12, 4, 42)
+    yc = np.stack([np.sin(Xc[:, 0]), Xc[:, 1] * Xc[:, 2]], axis=1)
+    todo = {
+        "function_sparse": (dict(landmarks=Xc[:30].copy(), ls=1.5, sigma=np.array([0.3, 0.6]), obs_variance=True,
+                                 predictor_with_uncertainty=True), Xc, yc),
+        "function_full": (dict(n_landmarks=0, ls=1.5, sigma=0.4, obs_variance=True, predictor_with_uncertainty=True),
+                          Xc[:60], yc[:60]),
+    }
+    cases = {}
+    for name, (kw, X, y) in todo.items():
+        est = mellon.FunctionEstimator(**kw)
+        est.fit(X, y)
+        pred = est.predict
+        nf = dict(noise_free=True) if pred.per_feature_sigma else {}
+        cases[name] = {"json": pred.to_json(), "Y": A(Yc).tolist(), "classname": type(pred).__name__,
+                       "mean": A(pred(Yc)).tolist(), "leverage": A(pred.leverage(Yc)).tolist(),
+                       "obs_variance": A(pred.obs_variance(Yc)).tolist(), "covariance": A(pred.covariance(Yc, **nf)).tolist(),
+                       "per_feature_sigma": bool(pred.per_feature_sigma)}
+    path = os.path.join(OUT, "reference_function_predictors.json")
+    with open(path, "w") as f:
+        json.dump(cases, f)
+    print(f"{path}: {os.path.getsize(path) / 1024:.1f} KiB, cases={sorted(cases)}")
+
+
 if __name__ == "__main__":
-    if "--predictors-only" in sys.argv:
+    if "--function-predictors-only" in sys.argv:
+        serialised_function_predictors()
+    elif "--predictors-only" in sys.argv:
         serialised_predictors()
     elif "--function-only" in sys.argv:
         function_estimator()

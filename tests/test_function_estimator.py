@@ -300,3 +300,25 @@ def test_random_configurations_against_the_oracle(be):
         if unc:
             nf = dict(noise_free=True) if est.predict.per_feature_sigma else {}
             assert rel(est.predict.covariance(Xq, **nf), O.function_covariance(fit, Xq)) < tol, case
+
+
+FUNCTION_PREDICTORS = os.path.join(os.path.dirname(__file__), "golden", "reference_function_predictors.json")
+
+
+@pytest.mark.parametrize("name", ["function_full", "function_sparse"])
+def test_reference_written_function_predictor_loads_and_predicts(be, name):
+    """Predictors fitted and serialised by the unmodified reference (oracle/make_golden.py --function-predictors-only):
+    the JSON text loads here and gives the reference's own numbers; the reverse direction is tools/check_json_interop.py."""
+    import json
+
+    with open(FUNCTION_PREDICTORS) as f:
+        case = json.load(f)[name]
+    pred = mb.Predictor.from_json_str(case["json"])
+    assert type(pred).__name__ == case["classname"] and bool(pred.per_feature_sigma) == case["per_feature_sigma"]
+    Y = np.asarray(case["Y"])
+    nf = dict(noise_free=True) if pred.per_feature_sigma else {}
+    tol = 1e-9 if type(be).__name__ == "FakeBackend" else 1e-6
+    assert rel(pred(Y), case["mean"]) < tol
+    assert rel(pred.leverage(Y), case["leverage"]) < tol
+    assert rel(pred.obs_variance(Y), case["obs_variance"]) < tol
+    assert rel(pred.covariance(Y, **nf), case["covariance"]) < tol
