@@ -476,6 +476,12 @@ static int run_trsm(int64_t n, int64_t m) {
   CK(cudaMemcpy(got.data(), X, got.size() * 8, cudaMemcpyDeviceToHost));
   double worst = 0, big = 0;
   for (size_t k = 0; k < (size_t)nref * m; k++) { big = fmax(big, fabs(hX[k])); const double e = fabs(got[k] - hX[k]); if (e > worst || e != e) worst = e; }
+  { int shown = 0;                           // the first few offenders: the column block tells which update step went wrong
+    for (size_t k = 0; k < (size_t)nref * m && shown < 8; k++)
+      if (!(fabs(got[k] - hX[k]) < 1e-11 * big)) {
+        printf("  X[%lld][%lld] (column block %lld): got %.17g, reference %.17g\n", (long long)(k / m), (long long)(k % m), (long long)((k % m) / TA), got[k], hX[k]);
+        shown++;
+      } }
   for (size_t k = (size_t)nref * m; k < got.size(); k++) if (got[k] != got[k] || fabs(got[k]) > 4 * big) worst = NAN;   // unchecked rows: sane at least
   printf("status %s; max |X - X_ref| / max |X_ref| = %.3e over the first rows (1024, or 256 at the timing sizes; forward substitution in long double as reference)\n",
          st ? "TIMEOUT in an mbarrier wait" : "ok", worst / big);
@@ -540,6 +546,10 @@ int main(int argc, char** argv) {
     long double acc = 0, bound = 0;
     for (int64_t k = 0; k < n; k++) { const long double a = hL[(size_t)k * r + i], b = hL[(size_t)k * r + j]; acc += a * b; bound += fabsl(a * b); }
     const double err = (double)(fabsl((long double)hG[(size_t)i * r + j] - acc) / bound);
+    if (!(err < 1e-14) && bad < 8)           // the first few offenders: which panel / column half / magnitude goes wrong
+      printf("  G[%lld][%lld] (A panel %lld row %lld, B panel %lld col %lld): got %.17g, reference %.17g, ratio %.6g\n", (long long)i,
+             (long long)j, (long long)(i / TA), (long long)(i % TA), (long long)(j / TB), (long long)(j % TB), hG[(size_t)i * r + j],
+             (double)acc, hG[(size_t)i * r + j] / (double)acc);
     if (!(err < 1e-14)) bad++;
     if (err > worst || err != err) worst = err;
     checked++;
