@@ -19,12 +19,19 @@ before the timed region, identically for every arm).  Rank 0 prints ONE JSON lin
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
 import sys
 import tempfile
 import time
+
+if "reference" in sys.argv[1:]:
+    # `--impl reference` under torch.distributed.run: the launcher exports OMP_NUM_THREADS=1 for every rank, which
+    # would starve the one rank that runs the CPU arm.  The thread pools read these at import, so set them first.
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
 
 import numpy as np
 
@@ -42,17 +49,38 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cells", type=int, default=1_000_000, help="N: total cells (all GPUs together)")
+    ap.add_argument("--cells", type=int, default=None, help="N: total cells (all GPUs together); default: the config's")
     ap.add_argument("--landmarks", type=int, default=5000, help="M")
-    ap.add_argument("--dims", type=int, default=50, help="D")
-    ap.add_argument("--cov", default="Matern52", choices=["Matern52", "Matern32", "ExpQuad"])
+    ap.add_argument("--dims", type=int, default=None, help="D; default: the config's")
+    ap.add_argument("--cov", default=None, choices=["Matern52", "Matern32", "ExpQuad"], help="default: the config's")
+    ap.add_argument("--config", default="headline", choices=["headline", "2", "3", "4", "5"],
+                    help="BASELINE.json configuration: headline = N=1e6, M=5000, D=50, Matern52, sparse Cholesky (the "
+                         "metric's workload); 2 = N=100k ExpQuad; 3 = headline cells with Nystroem rank=2000; "
+                         "4 = TimeSensitive N=500k D=20 10 time points Matern32 x ExpQuad(time); 5 = predict 5M queries")
+    ap.add_argument("--rank", type=int, default=None, help="Nystroem rank (int) -> gp_type sparse_nystroem")
     ap.add_argument("--cpu-sample", type=int, default=20_000, help="cells of the workload the CPU baseline times")
+    ap.add_argument("--no-linearity", action="store_true",
+                    help="reference arm: skip the one-off 25k / 50k / 100k series (BASELINE.md section 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region (A/B only)")
-    ap.add_argument("--predict-queries", type=int, default=1_000_000,
+    ap.add_argument("--predict-queries", type=int, default=None,
                     help="out-of-sample queries for the extra predict() measurement (BASELINE config 5 shape); 0 = skip")
-    return ap.parse_args()
+    args = ap.parse_args()
+    table = {  # cells, dims, cov, rank, predict queries, kind
+        "headline": (1_000_000, 50, "Matern52", None, 1_000_000, "density"),
+        "2": (100_000, 50, "ExpQuad", None, 0, "density"),
+        "3": (1_000_000, 50, "Matern52", 2000, 0, "density"),
+        "4": (500_000, 20, None, None, 0, "time"),
+        "5": (100_000, 50, "ExpQuad", None, 5_000_000, "predict"),
+    }
+    cells, dims, cov, rank, queries, args.kind = table[args.config]
+    args.cells = args.cells if args.cells is not None else cells
+    args.dims = args.dims if args.dims is not None else dims
+    args.cov = "Matern32 x ExpQuad(time)" if args.kind == "time" else (args.cov or cov)
+    args.rank = args.rank if args.rank is not None else rank
+    args.predict_queries = args.predict_queries if args.predict_queries is not None else queries
+    return args
 
 
 # ---- workload ------------------------------------------------------------------------------------
@@ -67,18 +95,33 @@ def pick_landmarks(x, m, seed=1):
     return np.ascontiguousarray(x[idx])
 
 
+TS_LS, TS_LS_TIME, TS_POINTS = 6.0, 1.5, 10   # config 4: length scales passed explicitly
+
+
+def make_times(n):
+    """Config 4: ten time points, equally many cells each, in blocks (times = repeat(arange(10), n / 10))."""
+    return np.repeat(np.arange(float(TS_POINTS)), -(-n // TS_POINTS))[:n]
+
+
 def workload_config(args, world):
+    gp_type = "sparse_nystroem rank=%d" % args.rank if args.rank else "sparse_cholesky"
+    est = "TimeSensitiveDensityEstimator.fit_predict" if args.kind == "time" else "DensityEstimator.fit_predict"
+    name = f"{est} N={args.cells} cells D={args.dims} M={args.landmarks} landmarks {args.cov} {gp_type} L-BFGS-B"
+    if args.kind == "predict":
+        name = (f"Predictor.mean on {args.predict_queries} out-of-sample queries (host in, host out) against the model "
+                f"fitted on N={args.cells} D={args.dims} M={args.landmarks} {args.cov} {gp_type}")
     return {
-        "workload": f"DensityEstimator.fit_predict N={args.cells} cells D={args.dims} M={args.landmarks} landmarks "
-                    f"{args.cov} sparse_cholesky L-BFGS-B",
+        "workload": name,
+        "baseline_config": args.config,
         "n_cells": args.cells,
         "n_landmarks": args.landmarks,
         "dims": args.dims,
         "cov": args.cov,
-        "gp_type": "sparse_cholesky",
+        "gp_type": gp_type,
         "optimizer": "L-BFGS-B (SciPy defaults, maxiter=500)",
         "inputs": "nn_distances (exact 1-NN) and landmarks (seeded row sample) precomputed outside the timed region",
-        "parallelism": f"cells row-sharded over {world} GPU(s); NCCL all-reduce of Gram and (loss, grad)",
+        "parallelism": f"cells row-sharded over {world} GPU(s) in whole chunks of the fixed 32-leaf reduction tree; "
+                       "Gram, (loss, grad) and L^T t summed through that tree (NCCL), bits independent of the GPU count",
         "l2_policy": "inputs larger than L2 (L is N x M float64 = %.1f GB per job)" % (args.cells * args.landmarks * 8 / 1e9),
     }
 
@@ -144,14 +187,20 @@ def oracle_cov(name):
     return getattr(O, name)
 
 
-def cpu_fit(x, lm, nn, cov_name):
+def cpu_fit(x, lm, nn, cov_name, rank=None, kind="density"):
     """The identical region on the host: Lp -> L -> z0 -> L-BFGS-B -> L z + mu, with the NumPy/SciPy/
-    sklearn restatement of the reference (the reference itself needs JAX, absent from this image)."""
+    sklearn restatement of the reference (the reference itself needs JAX, absent from this image).
+    kind "time": x carries the time in its last column, product covariance with explicit length scales."""
     from oracle import mellon_oracle as O
 
     timings = {}
     t0 = time.perf_counter()
-    fit = O.fit_density(x, cov_func_curry=oracle_cov(cov_name), landmarks=lm, nn_distances=nn, timings=timings)
+    if kind == "time":
+        cov = O.Matern32(TS_LS, active_dims=slice(None, -1)) * O.ExpQuad(TS_LS_TIME, active_dims=-1)
+        fit = O.fit_density(x, cov_func=cov, landmarks=lm, nn_distances=nn, d=x.shape[1] - 1, ls=TS_LS, timings=timings)
+    else:
+        fit = O.fit_density(x, cov_func_curry=oracle_cov(cov_name), landmarks=lm, nn_distances=nn, rank=rank,
+                            timings=timings)
     return time.perf_counter() - t0, fit, timings
 
 
@@ -170,48 +219,117 @@ def threads_used():
         return os.cpu_count()
 
 
+def nn_within_time_points(xt):
+    """Exact 1-NN distance of every cell among the cells of its own time point (time = last column)."""
+    from sklearn.neighbors import NearestNeighbors
+
+    out = np.empty(xt.shape[0])
+    for t in np.unique(xt[:, -1]):
+        idx = np.nonzero(xt[:, -1] == t)[0]
+        out[idx] = NearestNeighbors(n_neighbors=2).fit(xt[idx, :-1]).kneighbors(xt[idx, :-1])[0][:, 1]
+    return out
+
+
+def build_inputs(args):
+    """(x, landmarks): the synthetic cell matrix of the configuration (time as the last column for config 4)."""
+    x = make_cells(args.cells, args.dims)
+    if args.kind == "time":
+        x = np.ascontiguousarray(np.concatenate([x, make_times(args.cells)[:, None]], axis=1))
+    return x, pick_landmarks(x, args.landmarks)
+
+
+def sample_rows(args, n_total, ns):
+    """Rows of the bounded CPU sample: the first ns cells; strided for config 4 so that every time point is in it."""
+    ns = min(ns, n_total)
+    return np.arange(ns) if args.kind != "time" else np.arange(0, n_total, max(1, n_total // ns))[:ns]
+
+
 def run_reference(args):
     """`--impl reference`: the reference's CPU implementation of the path (oracle port; the reference
     cannot be installed here: it needs jax/jaxlib/jaxopt/pynndescent and there is no network) on a
-    bounded sample of the same workload.  Rank 0 alone works."""
+    bounded sample of the same workload, with every host thread.  Rank 0 alone works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from sklearn.neighbors import NearestNeighbors
+    from threadpoolctl import threadpool_limits
 
-    ns = min(args.cpu_sample, args.cells)
-    x = make_cells(args.cells, args.dims)
-    lm = pick_landmarks(x, args.landmarks)
-    xs = np.ascontiguousarray(x[:ns])
-    del x
+    from oracle import mellon_oracle as O
+
+    threadpool_limits(limits=os.cpu_count())
+    x, lm = build_inputs(args)
+    rows = sample_rows(args, x.shape[0], args.cpu_sample)
+    ns = rows.shape[0]
+    xs = np.ascontiguousarray(x[rows])
     # the sample's own exact 1-NN distances (host, outside the timed region)
-    nn = NearestNeighbors(n_neighbors=2).fit(xs).kneighbors(xs)[0][:, 1]
+    nn = nn_within_time_points(xs) if args.kind == "time" else NearestNeighbors(n_neighbors=2).fit(xs).kneighbors(xs)[0][:, 1]
+    metric, unit, units_per_step = METRIC, UNIT, ns
+    xq = None
+    if args.kind == "predict":
+        metric, unit = "queries/sec predict", "queries/s"
+        _, model, _ = cpu_fit(xs, lm, nn, args.cov)            # the fitted model (untimed); the path is predict()
+        xq = np.random.default_rng(2).random((min(args.cpu_sample, args.predict_queries), args.dims))
+        units_per_step = xq.shape[0]
     times, last = [], None
     for i in range(args.warmup + args.steps):
-        dt, fit, tm = cpu_fit(xs, lm, nn, args.cov)
+        if args.kind == "predict":
+            t0 = time.perf_counter()
+            O.predict_density(model, xs, xq)
+            dt, tm = time.perf_counter() - t0, {}
+        else:
+            dt, fit, tm = cpu_fit(xs, lm, nn, args.cov, args.rank, args.kind)
         if i >= args.warmup:
             times.append(dt)
             last = tm
     total = float(np.sum(times))
-    value = ns * len(times) / total
+    value = units_per_step * len(times) / total
     cores = threads_used()
+    sample = (f"{ns} cells of the workload ({'every time point, strided' if args.kind == 'time' else 'the first ones'}; all "
+              f"{args.landmarks} landmarks) per step; every stage is O(N), see `linearity`; host has {os.cpu_count()} "
+              f"logical CPUs, BLAS pool {cores} threads")
+    if args.kind == "predict":
+        sample = f"{units_per_step} of the {args.predict_queries} queries per step against a model fitted on {ns} cells"
+    linearity = None
+    if args.kind == "density" and not args.no_linearity and args.cells >= 100_000:
+        # BASELINE.md section 3: time the CPU arm at 25k / 50k / 100k once, check that it is linear in N, and label the
+        # N = 1e6 figure as an extrapolation (the reference formulation does not fit host RAM at 1e6 x 5000)
+        sizes, secs = [25_000, 50_000, 100_000], []
+        for n_l in sizes:
+            xl = np.ascontiguousarray(x[:n_l])
+            nl = NearestNeighbors(n_neighbors=2).fit(xl).kneighbors(xl)[0][:, 1]
+            secs.append(cpu_fit(xl, lm, nl, args.cov, args.rank)[0])
+        slope, icpt = np.polyfit(sizes, secs, 1)
+        linearity = {"cells": sizes, "seconds": [round(v, 2) for v in secs],
+                     "cells_per_s": [round(n_l / v, 1) for n_l, v in zip(sizes, secs)],
+                     "fit_seconds_per_cell": float(slope), "fit_intercept_s": float(icpt),
+                     "extrapolated_seconds_at_n_cells": float(slope * args.cells + icpt),
+                     "extrapolated_cells_per_s": float(args.cells / (slope * args.cells + icpt)),
+                     "note": "extrapolated: the CPU arm cannot hold N = 1e6 x M = 5000 temporaries in host RAM"}
     line = {
         "impl": "reference",
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"first {ns} cells of the workload (all {args.landmarks} landmarks), every stage "
-                                   f"is O(N): cells/s is size-independent; host has {os.cpu_count()} logical CPUs",
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample,
+                         "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
                          "stages_s": {k: round(float(v), 3) for k, v in (last or {}).items()}},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "linearity": linearity,
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
 # ---- CUDA arm -----------------------------------------------------------------------------------------
+def rel_metrics(a, b):
+    """The reference's own acceptance metric std(a - b) / std(b) (tests/test_density_estimator.py:30-44), and the
+    largest error relative to the largest value."""
+    a, b = np.asarray(a), np.asarray(b)
+    d = a - b
+    return float(np.std(d) / np.std(b)), float(np.max(np.abs(d)) / np.max(np.abs(b)))
+
+
 def run_b200(args):
     import mellon_b200 as mb
     from mellon_b200 import cov as C
@@ -224,20 +342,35 @@ def run_b200(args):
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     be = mb.get_backend()  # attaches the NCCL communicator when WORLD_SIZE > 1
-    cov_curry = getattr(C, args.cov)
 
-    x = make_cells(args.cells, args.dims)
-    lm = pick_landmarks(x, args.landmarks)
-    nn = be.nn_distances(x)  # exact 1-NN on the device, outside the timed region
+    x, lm = build_inputs(args)
+    if args.kind == "time":
+        # exact 1-NN within each time point on the device, outside the timed region
+        nn = np.empty(x.shape[0])
+        for t in range(TS_POINTS):
+            idx = np.nonzero(x[:, -1] == t)[0]
+            nn[idx] = be.nn_distances(np.ascontiguousarray(x[idx, :-1]))
+    else:
+        nn = be.nn_distances(x)  # exact 1-NN on the device, outside the timed region
     xd = be.upload(x, sharded=True)  # resident cell block of this rank
 
+    def make_estimator(lm_=lm, nn_=nn):
+        if args.kind == "time":
+            cov = C.Matern32(TS_LS, active_dims=slice(None, -1)) * C.ExpQuad(TS_LS_TIME, active_dims=-1)
+            return mb.TimeSensitiveDensityEstimator(cov_func=cov, ls=TS_LS, ls_time=TS_LS_TIME, d=args.dims, landmarks=lm_,
+                                                    nn_distances=nn_, check_rank=False)
+        cov_curry = getattr(C, args.cov)
+        return mb.DensityEstimator(cov_func_curry=cov_curry, landmarks=lm_, nn_distances=nn_, rank=args.rank,
+                                   check_rank=False)
+
     def step(x_in):
-        est = mb.DensityEstimator(cov_func_curry=cov_curry, landmarks=lm, nn_distances=nn, check_rank=False)
+        est = make_estimator()
         dens = est.fit_predict(x_in)
         return est, dens
 
     # --- device-resident arm: `value` -------------------------------------------------------------
-    for _ in range(args.warmup):
+    n_fit_steps = args.steps if args.kind != "predict" else 1
+    for _ in range(args.warmup if args.kind != "predict" else 1):
         est, dens = step(xd)
         del est
     be.prof_enable(True)
@@ -251,7 +384,7 @@ def run_b200(args):
     be.timer_start(0)
     nfev = []
     last_est = None
-    for _ in range(args.steps):
+    for _ in range(n_fit_steps):
         last_est = None  # frees the previous step's 40 GB factor before the next one is built
         est, dens = step(xd)
         nfev.append(int(est.opt_state.num_fun_eval))
@@ -261,42 +394,68 @@ def run_b200(args):
     ms = be.timer_stop(0)
     be.sync()
     dist.barrier()
-    clocks = sampler.stop() if rank == 0 else None
     launches = be.launch_count() - launches0
     prof = be.prof_read()
     be.prof_enable(False)
     ms = dist.host_max(ms)
-    ms_per_step = ms / args.steps
+    ms_per_step = ms / n_fit_steps
     value = args.cells / (ms_per_step * 1e-3)
     checksum = float(np.sum(dens))
+    digest = hashlib.sha256(np.ascontiguousarray(dens).tobytes()).hexdigest()
 
     # --- predict(): conditional-mean kernel K7 on out-of-sample queries (host in, host out) ---------
     predict = None
     if args.predict_queries > 0:
         q_total = args.predict_queries
-        xq = np.random.default_rng(2).random((q_total, args.dims))
+        xq = np.random.default_rng(2).random((q_total, args.dims + (1 if args.kind == "time" else 0)))
+        if args.kind == "time":
+            xq[:, -1] = np.random.default_rng(3).integers(0, TS_POINTS, q_total)
         predictor = last_est.predict          # builds the predictor: weights = Lp^-T z
         predictor(xq[:1024])                  # warm-up
+        n_pred = args.steps if args.kind == "predict" else 1
+        for _ in range(args.warmup if args.kind == "predict" else 0):
+            predictor(xq)
         be.prof_enable(True)
         be.prof_reset()
         dist.barrier()
         be.sync()
+        if args.kind == "predict":
+            launches0 = be.launch_count()
+            be.h2d_bytes = be.d2h_bytes = 0
         t0 = time.perf_counter()
-        pq = predictor(xq)
+        for _ in range(n_pred):
+            pq = predictor(xq)
         be.sync()
-        dt_q = dist.host_max(time.perf_counter() - t0)
+        dt_q = dist.host_max(time.perf_counter() - t0) / n_pred
         n_mv, ms_mv, _ = be.prof_read()["matvec"]
         be.prof_enable(False)
         predict = {"queries": q_total, "value": q_total / dt_q, "unit": "queries/s (host in, host out, all GPUs)",
-                   "k7_kernel_ms": ms_mv, "k7_launches": n_mv,
-                   "k7_elements_per_s": (q_total / max(world, 1)) * args.landmarks / (ms_mv * 1e-3) if ms_mv else None,
-                   "checksum": float(np.sum(pq))}
+                   "ms_per_pass": dt_q * 1e3, "k7_kernel_ms": ms_mv / n_pred, "k7_launches": n_mv // n_pred,
+                   "k7_elements_per_s": (q_total / max(world, 1)) * args.landmarks / (ms_mv / n_pred * 1e-3) if ms_mv else None,
+                   "checksum": float(np.sum(pq)), "sha256": hashlib.sha256(np.ascontiguousarray(pq).tobytes()).hexdigest()}
+        if args.kind == "predict":
+            launches = be.launch_count() - launches0
+            predict["h2d_bytes_per_step"] = int(dist.host_sum(be.h2d_bytes) / n_pred)
+            predict["d2h_bytes_per_step"] = int(dist.host_sum(be.d2h_bytes) / n_pred)
+            # parity of the predictions: the CPU oracle's conditional mean with the SAME fitted weights on a query sample
+            if rank == 0:
+                from oracle import mellon_oracle as O
+
+                qs = min(args.cpu_sample, q_total)
+                ref_q = O.conditional_mean(xq[:qs], lm, np.asarray(predictor.weights), float(predictor.mu),
+                                           oracle_cov(args.cov)(float(last_est.ls)))
+                predict["parity"] = dict(zip(("rel_std_err", "max_abs_err_over_max_abs"), rel_metrics(pq[:qs], ref_q)),
+                                         sample=f"first {qs} queries: K7 vs the oracle's mu + K(xq, xu) w with the same weights",
+                                         tolerance=1e-5)
+                predict["parity"]["ok"] = bool(max(predict["parity"]["rel_std_err"],
+                                                   predict["parity"]["max_abs_err_over_max_abs"]) < 1e-5)
         del predictor, xq
+    clocks = sampler.stop() if rank == 0 else None
     last_est = None
 
     # --- end-to-end arm: host buffers in, host result out -----------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.kind != "predict":
         xh = be.pinned_empty(x.shape)
         xh[...] = x
         step(xh)  # one warm-up through the host path
@@ -314,6 +473,58 @@ def run_b200(args):
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / args.steps}
         dist.barrier()
 
+    # --- parity, at every GPU count ----------------------------------------------------------------
+    # (1) the bounded sample of the workload through the CUDA path (all ranks, sharded) vs the CPU oracle (rank 0);
+    # (2) N > 1: rank 0 repeats the WHOLE workload alone (nothing sharded) and compares bits with the sharded result:
+    #     the fixed reduction tree makes fit_predict independent of the number of GPUs.
+    parity, cpu_baseline = None, None
+    if not args.no_cpu_baseline and args.kind != "predict":
+        rows = sample_rows(args, x.shape[0], args.cpu_sample)
+        ns = rows.shape[0]
+        xs, nns = np.ascontiguousarray(x[rows]), np.ascontiguousarray(nn[rows])
+        if args.kind == "time":
+            nns = nn_within_time_points(xs)            # the sample's own neighbours (a strided sample thins every time point)
+        est_s = make_estimator(lm, nns)
+        dens_s = est_s.fit_predict(xs)
+        one_gpu_same = None
+        if world > 1:
+            if rank == 0:
+                with be.replicated():
+                    dens_1 = make_estimator().fit_predict(x)
+                one_gpu_same = bool(hashlib.sha256(np.ascontiguousarray(dens_1).tobytes()).hexdigest() == digest)
+                one_gpu_maxdiff = float(np.max(np.abs(dens_1 - dens)))
+            dist.barrier()
+        if rank == 0:
+            dt, fit, tm = cpu_fit(xs, lm, nns, args.cov, args.rank, args.kind)
+            ref_s = np.asarray(fit.log_density_x)
+            rs, rm = rel_metrics(dens_s, ref_s)
+            parity = {
+                "sample": f"{ns} cells, all {args.landmarks} landmarks: CUDA fit_predict (sharded over {world} GPU(s)) vs "
+                          "the CPU oracle's, both at SciPy's default L-BFGS-B stop",
+                "metric": "rel_std_err = std(a - b) / std(b), the reference's own acceptance metric "
+                          "(tests/test_density_estimator.py:30-44); element-wise relative error is not judged because log "
+                          "densities cross zero on this workload",
+                "rel_std_err_log_density": rs, "max_abs_err_over_max_abs": rm,
+                "max_elementwise_rel_err": float(np.max(np.abs(dens_s - ref_s) / np.abs(ref_s))),
+                "min_abs_log_density": float(np.min(np.abs(ref_s))), "max_abs_log_density": float(np.max(np.abs(ref_s))),
+                "nfev_cuda": int(est_s.opt_state.num_fun_eval), "nfev_cpu": int(tm.get("nfev", -1)),
+                "tolerance": 1e-5,
+                "ok": bool(rs < 1e-5 and rm < 1e-5),
+                "log_density_sha256": digest,
+            }
+            if world > 1:
+                parity["vs_one_gpu"] = {"identical_bits": one_gpu_same, "max_abs_diff": one_gpu_maxdiff,
+                                        "how": "rank 0 refits the whole workload alone (unsharded) after the timed region"}
+                parity["ok"] = bool(parity["ok"] and one_gpu_same)
+            if world == 1:
+                cpu_baseline = {
+                    "value": ns / dt, "unit": UNIT, "cores": threads_used(), "kind": "port",
+                    "sample": f"{ns} cells of the workload (all {args.landmarks} landmarks); every stage is O(N) "
+                              f"(`bench.py --impl reference` prints the 25k / 50k / 100k series); {dt:.1f} s on "
+                              f"{os.cpu_count()} logical CPUs",
+                    "stages_s": {k: round(float(v), 3) for k, v in tm.items()},
+                }
+
     if rank != 0:
         return
 
@@ -327,67 +538,62 @@ def run_b200(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     n_cov, ms_cov, bytes_cov = prof["cov"]
     achieved = bytes_cov / (ms_cov * 1e-3) / 1e9 if ms_cov > 0 else 0.0
-    traffic = None
+    traffic, traffic_src = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
-    except (OSError, ValueError):
+        tr = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        # static: one `ncu --set full` capture of this kernel at N = 1e6 on one GPU; per launch it scales with the cells
+        # a launch covers, so it is scaled by this run's algorithmic bytes per launch over the captured launch's
+        ref_alg = float(tr.get("algorithmic_bytes_per_launch", 0.0))
+        if ref_alg > 0 and n_cov:
+            traffic = float(tr["dram_bytes_per_launch"]) * (bytes_cov / n_cov) / ref_alg
+            traffic_src = (f"static: {tr.get('source', 'profiles/k1_traffic.json')} ({tr['dram_bytes_per_launch']:.4g} B for "
+                           f"{ref_alg:.4g} algorithmic B), scaled to this run's bytes per launch; not measured in this run")
+    except (OSError, ValueError, KeyError):
         pass
     roofline = {
         "kernel": "cov_mma_kernel (K1: fused pairwise distance + covariance, K_NM build; FP64-issue bound, see DESIGN.md)",
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-        "frac": achieved / hbm_peak if hbm_peak else None, "traffic": traffic, "peak_source": peak_src,
-        "launches": n_cov, "avg_launch_ms": ms_cov / max(n_cov, 1),
+        "frac": achieved / hbm_peak if hbm_peak else None, "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": peak_src, "launches": n_cov, "avg_launch_ms": ms_cov / max(n_cov, 1),
         "algorithmic_bytes_per_launch": bytes_cov / max(n_cov, 1),
     }
     n_lg, ms_lg, bytes_lg = prof["lossgrad"]
     n_gm, ms_gm, flops_gm = prof["gemm"]
+    n_i8, ms_i8, flops_i8 = prof.get("gemm_i8", (0, 0.0, 0.0))
     kernels = {
-        "k1_cov_build": {"launches": n_cov, "ms_per_step": ms_cov / args.steps, "share": ms_cov / ms},
-        "k5_loss_grad": {"launches": n_lg, "ms_per_step": ms_lg / args.steps, "share": ms_lg / ms,
+        "k1_cov_build": {"launches": n_cov, "ms_per_step": ms_cov / n_fit_steps, "share": ms_cov / ms},
+        "k5_loss_grad": {"launches": n_lg, "ms_per_step": ms_lg / n_fit_steps, "share": ms_lg / ms,
                          "achieved_GBps": bytes_lg / (ms_lg * 1e-3) / 1e9 if ms_lg else None,
                          "hbm_frac": bytes_lg / (ms_lg * 1e-3) / 1e9 / hbm_peak if ms_lg else None},
-        "fp64_gemm (K3 trsm + K4 gram + K2 updates)": {
-            "launches": n_gm, "ms_per_step": ms_gm / args.steps, "share": ms_gm / ms,
+        "fp64_gemm (DMMA: K3 trsm + K2 updates, K4 when int8 is off)": {
+            "launches": n_gm, "ms_per_step": ms_gm / n_fit_steps, "share": ms_gm / ms,
             "achieved_TFLOPs": flops_gm / (ms_gm * 1e-3) / 1e12 if ms_gm else None},
+        "int8_slice_gemm (tcgen05 kind::i8 digit slices, float64-equivalent)": {
+            "launches": n_i8, "ms_per_step": ms_i8 / n_fit_steps, "share": ms_i8 / ms,
+            "achieved_f64_equiv_TFLOPs": flops_i8 / (ms_i8 * 1e-3) / 1e12 if ms_i8 else None},
     }
+    n_evals = max(1, int(np.sum(nfev)))
+    per_eval = {"evaluations_per_step": float(np.mean(nfev)),
+                "k5_kernel_ms_per_eval": ms_lg / max(n_lg, 1),
+                "note": "host + launch + collective per evaluation = (L-BFGS-B wall - K5 kernel time) / evaluations, see "
+                        "tools/trace_step.py"}
 
-    cpu_baseline = None
-    parity = None
-    if not args.no_cpu_baseline and world == 1:
-        xs, lms, nns, ns = cpu_sample(args, x, lm, nn)
-        dt, fit, tm = cpu_fit(xs, lms, nns, args.cov)
-        # parity on the very sample the CPU arm just fitted: the same cells through the CUDA path
-        dens_s = mb.DensityEstimator(cov_func_curry=cov_curry, landmarks=lms, nn_distances=nns,
-                                     check_rank=False).fit_predict(xs)
-        ref_s = np.asarray(fit.log_density_x)
-        diff = dens_s - ref_s
-        parity = {
-            "sample": f"first {ns} cells, all {args.landmarks} landmarks: CUDA fit_predict vs the CPU oracle's",
-            # the reference's own acceptance metric (tests/test_density_estimator.py:30-44): std(a - b) / std(b)
-            "rel_std_err_log_density": float(np.std(diff) / np.std(ref_s)),
-            "max_abs_err_over_max_abs": float(np.max(np.abs(diff)) / np.max(np.abs(ref_s))),
-            # element-wise relative error: log densities cross zero on this workload, so this one is dominated by
-            # the cells whose log density is ~0 (reported for completeness, not judged)
-            "max_elementwise_rel_err": float(np.max(np.abs(diff) / np.abs(ref_s))),
-            "min_abs_log_density": float(np.min(np.abs(ref_s))), "max_abs_log_density": float(np.max(np.abs(ref_s))),
-            "tolerance": 1e-5,
-        }
-        parity["ok"] = bool(parity["rel_std_err_log_density"] < 1e-5 and parity["max_abs_err_over_max_abs"] < 1e-5)
-        cpu_baseline = {
-            "value": ns / dt, "unit": UNIT, "cores": threads_used(), "kind": "port",
-            "sample": f"first {ns} cells of the workload (all {args.landmarks} landmarks, their nn_distances taken "
-                      f"from the full set); every stage is O(N) so cells/s is size-independent; {dt:.1f} s on "
-                      f"{os.cpu_count()} logical CPUs",
-            "stages_s": {k: round(float(v), 3) for k, v in tm.items()},
-        }
-
+    metric, unit = METRIC, UNIT
+    if args.kind == "predict":
+        metric, unit, value, ms_per_step = "queries/sec predict", "queries/s", predict["value"], predict["ms_per_pass"]
+        e2e = {"value": predict["value"], "unit": unit, "h2d_bytes_per_step": predict["h2d_bytes_per_step"],
+               "d2h_bytes_per_step": predict["d2h_bytes_per_step"],
+               "note": "predict() takes host queries and returns host results: the public call IS the end-to-end path; "
+                       "the kernel-only rate is predict.k7_elements_per_s"}
+        parity = predict.get("parity")
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+        "per_evaluation": per_eval,
         "predict": predict, "cpu_baseline": cpu_baseline, "parity": parity, "lbfgsb": {"nfev_per_step": nfev, "nit_last": nit},
-        "log_density_checksum": checksum,
+        "log_density_checksum": checksum, "log_density_sha256": digest,
     }
     print(json.dumps(line))
 

@@ -18,10 +18,15 @@
  *     non-positive pivot) — the host raises the reference's ValueError
  *     (decomposition.py:116-122) on it.
  *   - one context drives ONE GPU; one process per GPU.  With a communicator attached
- *     (mb_comm_init) the cell axis is sharded across ranks (each rank holds a block of
- *     rows of x / K_NM / L) and the entry points marked [all-reduce] sum their result
- *     over ranks with NCCL (sum, f64, on the device) before returning it, so every
- *     rank sees identical bits.
+ *     (mb_comm_init) the cell axis is sharded across ranks: each rank holds the block of
+ *     rows of x / K_NM / L that mb_row_block assigns to it and marks those matrices with
+ *     mb_mat_set_shard.  The entry points marked [cell sum] add over the cells of ALL
+ *     ranks when their operand is so marked (and over the local rows only when it is
+ *     not: a replicated matrix is never summed twice), and every rank sees identical bits.
+ *   - [cell sum] results do not depend on the number of ranks: the global cell axis is cut
+ *     into 32 chunks, a chunk is summed in an order that depends on the chunk alone, and
+ *     the 32 chunk sums are combined by one fixed pairwise tree (within a rank and across
+ *     ranks alike).  mb_row_block puts rank boundaries on chunk boundaries.
  */
 #ifndef MELLON_B200_H
 #define MELLON_B200_H
@@ -118,7 +123,15 @@ int mb_comm_unique_id(unsigned char* out128);
 int mb_comm_init(mb_ctx* ctx, const unsigned char* id128, int rank, int world);
 int mb_comm_destroy(mb_ctx* ctx);
 int mb_comm_info(mb_ctx* ctx, int* rank, int* world);
-/* sum a device matrix over ranks in place (no-op without a communicator) */
+/* Row block [*row_lo, *row_hi) of rank `rank` of `world` for a cell axis of `global_rows` rows: whole chunks of
+ * *chunk_rows = ceil(global_rows / 32) rows, chunks [32 rank / world, 32 (rank + 1) / world).  Pure function. */
+int mb_row_block(int64_t global_rows, int rank, int world, int64_t* row_lo, int64_t* row_hi, int64_t* chunk_rows);
+/* Mark `m` as rows [row_lo, row_lo + rows) of a matrix of `global_rows` rows whose cell axis is sharded over the
+ * ranks (global_rows < 0 clears the mark).  With a communicator attached the block must be the one mb_row_block
+ * gives this rank. */
+int mb_mat_set_shard(mb_mat* m, int64_t global_rows, int64_t row_lo);
+/* sum a device matrix over ranks in place (no-op without a communicator); plain NCCL all-reduce, rank-count
+ * dependent rounding: not used on the fit path any more (the [cell sum] entry points reduce through the fixed tree) */
 int mb_comm_allreduce(mb_ctx* ctx, mb_mat* a);
 /* gather equally-sized row blocks: out(world*rows, cols) <- a(rows, cols) of each rank */
 int mb_comm_allgather(mb_ctx* ctx, const mb_mat* a, mb_mat* out);
@@ -150,6 +163,11 @@ int mb_mat_copy_cols(mb_ctx* ctx, const mb_mat* src, int64_t c0, int64_t ncols, 
 int mb_mat_symmetrize(mb_ctx* ctx, mb_mat* a);
 /* a *= s                          conditional.py:139-181 (`A / sigma2`), :296-300 */
 int mb_mat_scale(mb_ctx* ctx, mb_mat* a, double s);
+/* a <- a + b | a * b (op = MB_OP_ADD | MB_OP_MUL; b == NULL: the scalar `value` instead of b) or a ** value
+ * (MB_OP_POW), elementwise: base_cov.py:309-315, 375-381, 449-453 for expressions too large for ONE covariance
+ * program (more than MB_MAX_LEAVES leaves): the sub-expressions are built by mb_cov_build and combined here, on
+ * the device. */
+int mb_mat_combine(mb_ctx* ctx, int op, mb_mat* a, const mb_mat* b, double value);
 /* out(i) = sum_j a(i, j)^2        conditional.py:417,436,712,731,941,959 (`arraysum(square(A), axis=0)`
  * on the transposed layout this library keeps) */
 int mb_mat_row_sumsq(mb_ctx* ctx, const mb_mat* a, mb_mat* out);
@@ -197,15 +215,17 @@ int mb_lowrank_standard(mb_ctx* ctx, const mb_kprog* prog, const mb_mat* x, cons
                         const mb_mat* Lp, mb_mat* L);
 
 /* ---- K4: Gram contraction over the cell axis ------------------------------------------- */
-/* G = L^T L (r x r, full symmetric)  [all-reduce]
+/* G = L^T L (r x r, full symmetric)  [cell sum]
  * parameters.py:896 (Ridge normal equations), conditional.py:61 (A A^T),
  * decomposition.py:259 (QR of K_NM via its Gram). */
 int mb_gram(mb_ctx* ctx, const mb_mat* L, mb_mat* G);
-/* b = L^T t (r x 1)  [all-reduce]   parameters.py:896, conditional.py:64 (`dot(A, r_l)`) */
+/* b = L^T t (r x 1)  [cell sum]   parameters.py:896, conditional.py:64 (`dot(A, r_l)`) */
 int mb_gemv_t(mb_ctx* ctx, const mb_mat* L, const mb_mat* t, mb_mat* b);
-/* z0 = (L^T L + I)^-1 L^T t  [all-reduce inside]   parameters.py:877-896 */
+/* z0 = (L^T L + I)^-1 L^T t  [cell sums inside]   parameters.py:877-896 */
 int mb_ridge_init(mb_ctx* ctx, const mb_mat* L, const mb_mat* t, double* z0_host);
-/* C = alpha op(A) op(B) + beta C ; op = transpose when the flag is 1 (local, no reduce) */
+/* C = alpha op(A) op(B) + beta C ; op = transpose when the flag is 1.  With trans_a = 1, trans_b = 0 and A, B marked
+ * as row blocks of sharded matrices the product contracts over the cells: [cell sum] (alpha = 1, beta = 0 only;
+ * conditional.py:61-64 `dot(A, y)` on the transposed layout).  Otherwise local. */
 int mb_gemm(mb_ctx* ctx, int trans_a, int trans_b, double alpha, const mb_mat* A,
             const mb_mat* B, double beta, mb_mat* C);
 
@@ -213,20 +233,21 @@ int mb_gemm(mb_ctx* ctx, int trans_a, int trans_b, double alpha, const mb_mat* A
  * One fused pass over the local rows of L:
  *   f = L z + mu ; A = exp(f + V)
  *   loss = 1/2 |z|^2 + (k/2) log 2pi - (sum_i (f_i - A_i) + sum_vdr)
- *   grad = z + L^T (A - 1)                                     [all-reduce of r+1 doubles]
+ *   grad = z + L^T (A - 1)                                     [cell sum of r+1 doubles]
  * inference.py:35-48, 51-69, 72-92, 167-192 + jax.value_and_grad (inference.py:285).
  * `V` is the per-cell vector of inference.py:84; `sum_vdr` the global sum of :85. */
 int mb_loss_grad(mb_ctx* ctx, const mb_mat* L, const mb_mat* V, double sum_vdr, double mu,
                  double k, const double* z_host, double* loss, double* grad_host);
 /* f = L z + mu for the local rows    inference.py:66-67, 341-354 */
 int mb_transform(mb_ctx* ctx, const mb_mat* L, const double* z_host, double mu, double* f_host);
-/* diag(I + L^T diag(A) L)  [all-reduce]   inference.py:311-317 in closed form */
+/* diag(I + L^T diag(A) L)  [cell sum]   inference.py:311-317 in closed form */
 int mb_hess_diag(mb_ctx* ctx, const mb_mat* L, const mb_mat* V, double mu, const double* z_host,
                  double* diag_host);
 
 /* ---- symmetric eigen-decomposition (Nystroem paths) -------------------------------------
  * a <- eigenvectors (columns, ascending eigenvalues in w).  decomposition.py:50
- * (`eigh`).  Jacobi-free: tridiagonalisation is hand-written; see DESIGN.md. */
+ * (`eigh`).  LIBRARY CALL: cuSOLVER Dsyevd (dlopen'ed), the one device routine of this
+ * library that is not hand-written; see DESIGN.md. */
 int mb_syevd(mb_ctx* ctx, mb_mat* a, mb_mat* w);
 
 #ifdef __cplusplus

@@ -81,6 +81,8 @@ SIGNATURES = {
     "mb_comm_init": (_i, [_vp, C.c_char_p, _i, _i]),
     "mb_comm_destroy": (_i, [_vp]),
     "mb_comm_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    "mb_row_block": (_i, [_i64, _i, _i, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "mb_mat_set_shard": (_i, [_vp, _i64, _i64]),
     "mb_comm_allreduce": (_i, [_vp, _vp]),
     "mb_comm_allgather": (_i, [_vp, _vp, _vp]),
     "mb_mat_alloc": (_i, [_vp, _i64, _i64, C.POINTER(_vp)]),
@@ -98,6 +100,7 @@ SIGNATURES = {
     "mb_mat_copy_cols": (_i, [_vp, _vp, _i64, _i64, _vp]),
     "mb_mat_symmetrize": (_i, [_vp, _vp]),
     "mb_mat_scale": (_i, [_vp, _vp, _d]),
+    "mb_mat_combine": (_i, [_vp, _i, _vp, _vp, _d]),
     "mb_mat_row_sumsq": (_i, [_vp, _vp, _vp]),
     "mb_cov_build": (_i, [_vp, _pprog, _vp, _vp, _vp]),
     "mb_cov_diag": (_i, [_vp, _pprog, _vp, _vp]),

@@ -12,6 +12,7 @@ without a GPU against a test double that lives under ``tests/``.
 
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import logging
 import os
@@ -39,11 +40,19 @@ def get_backend():
     return _backend
 
 
+N_CHUNKS = 32  # leaves of the library's fixed reduction tree over the cell axis (MB_NCHUNK)
+
+
 def row_block(n, rank, world):
-    """Contiguous row block of rank ``rank``: equal blocks of ceil(n / world) rows."""
-    per = -(-n // world) if world > 0 else n
-    lo = min(n, rank * per)
-    hi = min(n, lo + per)
+    """Contiguous row block ``(lo, hi, per)`` of rank ``rank``: whole chunks of ceil(n / 32) rows, chunks
+    [32 rank / world, 32 (rank + 1) / world) — the same rule as ``mb_row_block`` in the C ABI, so that rank
+    boundaries are leaves of the library's reduction tree and every sum over cells has the same bits for any
+    number of ranks.  ``per`` is the largest block of any rank (padding unit of the row gathers)."""
+    world = max(int(world), 1)
+    cr = max(1, -(-n // N_CHUNKS))
+    lo = min(n, (rank * N_CHUNKS // world) * cr)
+    hi = min(n, ((rank + 1) * N_CHUNKS // world) * cr)
+    per = max(1, -(-N_CHUNKS // world)) * cr
     return lo, hi, per
 
 
@@ -173,6 +182,19 @@ class CudaBackend:
             self.lib.mb_ctx_destroy(self.ctx)
             self.ctx = None
 
+    @contextlib.contextmanager
+    def replicated(self):
+        """Inside the block this rank works ALONE on whole matrices even though a communicator is attached:
+        nothing is sharded, nothing is marked as a row block, so the library sums over local rows only.  Used to
+        reproduce the one-GPU result inside a multi-GPU job (bench.py / tools/check_multi_gpu.py compare its bits
+        with the sharded result: the reduction tree makes them identical)."""
+        saved = (self.rank, self.world, getattr(self, "_replicated", False))
+        self.rank, self.world, self._replicated = 0, 1, True
+        try:
+            yield self
+        finally:
+            self.rank, self.world, self._replicated = saved
+
     # -- bookkeeping --------------------------------------------------------------------------
     def sync(self):
         nat.check(self.lib.mb_ctx_sync(self.ctx), "mb_ctx_sync")
@@ -238,7 +260,12 @@ class CudaBackend:
             self.lib.mb_mat_free(self.ctx, h)
 
     def empty(self, rows, cols, global_rows=None, row_lo=0, vector=False):
-        return DeviceArray(self, self._alloc(rows, cols), (rows, cols), global_rows, row_lo, vector)
+        """Uninitialised device matrix; with ``global_rows`` it is this rank's row block of a matrix whose
+        cell axis is sharded, and the library is told so (sums over its rows then span all ranks)."""
+        d = DeviceArray(self, self._alloc(rows, cols), (rows, cols), global_rows, row_lo, vector)
+        if global_rows is not None and not getattr(self, "_replicated", False):
+            nat.check(self.lib.mb_mat_set_shard(d._h, int(global_rows), int(row_lo)), "mb_mat_set_shard")
+        return d
 
     def upload(self, a, sharded=False):
         """Copy a host array to the device.  ``sharded`` keeps only this rank's row block."""
@@ -290,25 +317,31 @@ class CudaBackend:
         src = self.upload(pad)
         dst = self.empty(per * self.world, l2.shape[1])
         nat.check(self.lib.mb_comm_allgather(self.ctx, src._h, dst._h), "mb_comm_allgather")
-        out = self._download_local(dst)[:n]
+        padded = self._download_local(dst)
+        # blocks are whole reduction chunks, so their sizes may differ by a chunk: cut each rank's rows out
+        out = np.concatenate([padded[r * per: r * per + (hi - lo)]
+                              for r in range(self.world) for lo, hi, _ in [row_block(n, r, self.world)]], axis=0)
         return out[:, 0] if vec else out
 
     # -- covariance programs --------------------------------------------------------------------
-    def _prog(self, cov_func, n_cols):
+    def _prog(self, cov_func, n_cols, stock_root=False):
         """Compiled covariance program of ``cov_func``, cached per (object, width, STATE): covariances are
         mutable (the reference's tests assign ``cov.active_dims`` after a first evaluation), so a cached program
         is reused only while the serialised expression tree is unchanged."""
         from .base_cov import compile_covariance
 
+        quiet, logger.disabled = logger.disabled, True   # __getstate__ warns about user classes: once is enough
         try:
             fingerprint = repr(cov_func.__getstate__())
         except Exception:  # user-defined subclasses without serialisation: never cache
             fingerprint = None
-        key = (id(cov_func), int(n_cols))
+        finally:
+            logger.disabled = quiet
+        key = (id(cov_func), int(n_cols), bool(stock_root))
         hit = self._progs.get(key)
         if hit is not None and hit[0] is cov_func and fingerprint is not None and hit[2] == fingerprint:
             return hit[1]
-        prog = compile_covariance(cov_func, int(n_cols))
+        prog = compile_covariance(cov_func, int(n_cols), stock_root=stock_root)
         self._progs[key] = (cov_func, prog, fingerprint)
         return prog
 
@@ -321,22 +354,63 @@ class CudaBackend:
         except NotCompilable:
             return False
 
-    def cov(self, cov_func, x, y, sharded=False):
-        """K = cov_func(x, y) on the device (K1).  ``sharded``: x is the cell matrix."""
-        from .base_cov import NotCompilable
+    def cov(self, cov_func, x, y, sharded=False, stock_root=False):
+        """K = cov_func(x, y) on the device (K1).  ``sharded``: x is the cell matrix.
+
+        An expression that does not fit ONE device program (more than 4 leaves / 16 ops, or a user-defined kernel
+        somewhere inside) is split at its root: the operands are built separately — recursively, each by K1 when it
+        compiles — and combined on the device (``mb_mat_combine``).  Only a user-defined ``k`` itself runs on the
+        host (its result is uploaded); no stock kernel is ever evaluated there."""
+        from .base_cov import NotCompilable, is_stock_pair, Add, Mul, Pow
+        from .util import select_active_dims
 
         xd = self.upload(x, sharded=sharded)
         yd = xd if y is x else self.upload(y)
         try:
-            prog = self._prog(cov_func, xd.local_shape[1])
+            prog = self._prog(cov_func, xd.local_shape[1], stock_root=stock_root)
         except NotCompilable:
-            # a user-defined Covariance subclass: run the user's own `k` and upload the result
+            if is_stock_pair(cov_func) or (stock_root and isinstance(cov_func, (Add, Mul, Pow))):
+                xs = select_active_dims(self._host_rows(x, xd), cov_func.active_dims)
+                ys = xs if y is x else select_active_dims(self._host_rows(y, yd), cov_func.active_dims)
+                K = self.cov(cov_func.left, xs, ys, sharded=False)
+                if isinstance(cov_func, Pow):
+                    op, other, value = nat.OP_POW, None, float(cov_func.right)
+                elif callable(cov_func.right):
+                    op = nat.OP_ADD if isinstance(cov_func, Add) else nat.OP_MUL
+                    other, value = self.cov(cov_func.right, xs, ys, sharded=False), 0.0
+                else:
+                    op = nat.OP_ADD if isinstance(cov_func, Add) else nat.OP_MUL
+                    other, value = None, float(cov_func.right)
+                nat.check(self.lib.mb_mat_combine(self.ctx, op, K._h, other._h if other is not None else None, value),
+                          "mb_mat_combine")
+                if xd.sharded:
+                    K = self._mark_rows(K, xd)
+                return K
+            # a user-defined Covariance subclass: run the user's own `k` on this rank's rows and upload the result
             logger.warning("Covariance %r has no device program; evaluating its k() on the host.", cov_func)
-            return self.upload(np.asarray(cov_func.k(np.asarray(x), np.asarray(y))), sharded=sharded)
+            Kh = np.asarray(cov_func.k(self._host_rows(x, xd), self._host_rows(y, yd)), dtype=np.float64)
+            K = self.upload(Kh)
+            return self._mark_rows(K, xd) if xd.sharded else K
         K = self.empty(xd.local_shape[0], yd.local_shape[0], global_rows=xd.shape[0] if xd.sharded else None,
                        row_lo=xd.row_lo)
         nat.check(self.lib.mb_cov_build(self.ctx, C.byref(prog.struct), xd._h, yd._h, K._h), "mb_cov_build")
         return K
+
+    def _host_rows(self, a, d):
+        """Host copy of the rows of ``a`` that the device array ``d`` (its upload) holds on this rank."""
+        if isinstance(a, DeviceArray):
+            out = self._download_local(a)
+            return out[:, 0] if a._vector else out
+        a = np.asarray(a, dtype=np.float64)
+        a2 = a.reshape(-1, 1) if a.ndim == 1 else a
+        return a2[d.row_lo: d.row_lo + d.local_shape[0]] if d.sharded else a2
+
+    def _mark_rows(self, K, like):
+        """Re-label a locally built matrix as this rank's row block of a sharded one (rows as in ``like``)."""
+        out = DeviceArray(self, K._h, K.local_shape, like.shape[0], like.row_lo)
+        K._h = None
+        nat.check(self.lib.mb_mat_set_shard(out._h, int(like.shape[0]), int(like.row_lo)), "mb_mat_set_shard")
+        return out
 
     def nn_distances(self, x, return_index=False):
         """Exact nearest-neighbour distance of every row of ``x`` (brute force on the device).
@@ -440,7 +514,7 @@ class CudaBackend:
 
     def gemm(self, A, B, trans_a=False, trans_b=False, alpha=1.0, beta=0.0, out=None, reduce=False):
         """``alpha op(A) op(B) + beta out``.  ``reduce``: both operands are row-sharded and contracted
-        over the cell axis (op(A) = A^T) — the partial products are all-reduced."""
+        over the cell axis (op(A) = A^T) — summed over the cells of all ranks by the library."""
         A = self.upload(A)
         B = self.upload(B, sharded=reduce)
         m = A.local_shape[1] if trans_a else A.local_shape[0]
@@ -448,10 +522,11 @@ class CudaBackend:
         if out is None:
             keep_rows = A.sharded and not trans_a
             out = self.empty(m, n, global_rows=A.shape[0] if keep_rows else None, row_lo=A.row_lo if keep_rows else 0)
+        if reduce and not (A.sharded and B.sharded and trans_a and not trans_b):
+            raise ValueError("reduce=True contracts A^T B over the cells of two row-sharded operands")
+        # with sharded operands and trans_a the library sums over the cells of all ranks (fixed tree)
         nat.check(self.lib.mb_gemm(self.ctx, int(trans_a), int(trans_b), float(alpha), A._h, B._h, float(beta),
                                    out._h), "mb_gemm")
-        if reduce:
-            self.allreduce(out)
         return out
 
     def eye(self, n):
@@ -558,15 +633,18 @@ class CudaBackend:
         w = np.asarray(weights, dtype=np.float64)
         vec = w.ndim == 1
         based = self.upload(base)
-        try:
-            prog = self._prog(cov_func, based.local_shape[1])
-        except NotCompilable:
-            K = np.asarray(cov_func.k(xq, np.asarray(base)))
-            return mu + K.dot(w)
         wd = self.upload(w.reshape(w.shape[0], -1))
         n = xq.shape[0]
         lo, hi, _ = row_block(n, self.rank, self.world) if self.world > 1 else (0, n, n)
         blk = np.ascontiguousarray(xq[lo:hi])
+        try:
+            prog = self._prog(cov_func, based.local_shape[1])
+        except NotCompilable:
+            # no single device program: build K (split at the root, see `cov`) and multiply on the device
+            out = mu + self.gemm(self.cov(cov_func, blk, based), wd).numpy()
+            if self.world > 1:
+                out = self.gather_rows(out, n)
+            return out[:, 0] if vec else out
         out = np.empty((hi - lo, wd.local_shape[1]), dtype=np.float64)
         nat.check(self.lib.mb_predict_mean(self.ctx, C.byref(prog.struct), nat.ptr(blk), hi - lo, blk.shape[1],
                                            based._h, wd._h, float(mu), nat.ptr(out)), "mb_predict_mean")

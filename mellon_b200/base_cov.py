@@ -61,8 +61,16 @@ def _resolve(cols, active_dims):
         raise ValueError(f"active_dims {active_dims!r} do not fit an input with {len(cols)} columns") from e
 
 
-def compile_covariance(cov, n_cols):
-    """Flatten ``cov`` for inputs with ``n_cols`` columns into a :class:`CompiledProgram`."""
+def is_stock_pair(node):
+    """An Add / Mul / Pow node whose ``k`` is the stock one (not overridden by a user subclass)."""
+    return isinstance(node, CovariancePair) and type(node).k in (Add.k, Mul.k, Pow.k)
+
+
+def compile_covariance(cov, n_cols, stock_root=False):
+    """Flatten ``cov`` for inputs with ``n_cols`` columns into a :class:`CompiledProgram`.
+
+    ``stock_root``: the call comes from the stock ``k`` of the root node itself (a user subclass that extends a
+    stock kernel and calls ``super().k``), so the root is compiled as its stock kind whatever ``type(cov).k`` is."""
     ops, dims = [], []
     depth = [0, 0]  # current, max
 
@@ -72,7 +80,8 @@ def compile_covariance(cov, n_cols):
 
     def visit(node, cols):
         leaf_kind = getattr(type(node), "_kind", None)
-        if leaf_kind is not None and type(node).k is _LEAF_K.get(leaf_kind):
+        forced = stock_root and node is cov
+        if leaf_kind is not None and (forced or type(node).k is _LEAF_K.get(leaf_kind)):
             sel = _resolve(cols, node.active_dims)
             all_dims = len(sel) == n_cols and np.array_equal(sel, np.arange(n_cols))
             op = nat.KOp(nat.OP_LEAF, leaf_kind, float(node.ls), float(getattr(node, "alpha", 1.0)), 0.0,
@@ -82,7 +91,7 @@ def compile_covariance(cov, n_cols):
             ops.append(op)
             push()
             return
-        if isinstance(node, CovariancePair) and type(node).k in (Add.k, Mul.k, Pow.k):
+        if is_stock_pair(node) or (forced and isinstance(node, (Add, Mul, Pow))):
             sel = _resolve(cols, node.active_dims)
             visit(node.left, sel)
             if isinstance(node, Pow):
@@ -134,7 +143,7 @@ class Covariance(ABC):
         y = np.asarray(y, dtype=np.float64)
         if x.ndim != 2 or y.ndim != 2:
             raise ValueError("covariance inputs must be 2-dimensional (samples x features)")
-        return get_backend().cov(self, x, y).numpy()
+        return get_backend().cov(self, x, y, stock_root=True).numpy()
 
     def k_grad(self, x):
         """Gradient of k(x, y) w.r.t. y: callable y -> (n, m, d).  Central differences of the
@@ -164,6 +173,12 @@ class Covariance(ABC):
         be = get_backend()
         if be.supports(self, x.shape[-1]):
             return be.cov_diag(self, x)
+        if is_stock_pair(self):
+            # too large for one device program (or a user kernel inside): the diagonals of the operands, combined
+            xs = select_active_dims(x, self.active_dims)
+            right = np.asarray(self.right.diag(xs)) if callable(self.right) else self.right
+            return self._combine(np.asarray(self.left.diag(xs)), right)
+        # a user-defined kernel: its own k, one point at a time
         return np.array([np.asarray(self.k(x[i : i + 1], x[i : i + 1]))[0, 0] for i in range(x.shape[0])])
 
     def __add__(self, other):
@@ -248,15 +263,10 @@ class CovariancePair(Covariance):
         raise NotImplementedError
 
     def k(self, x, y):
-        try:
-            return self._device_k(x, y)
-        except NotCompilable:
-            # evaluate the operands separately (each on the device when it can) and combine
-            xs = select_active_dims(np.asarray(x), self.active_dims)
-            ys = select_active_dims(np.asarray(y), self.active_dims)
-            left = np.asarray(self.left(xs, ys))
-            right = np.asarray(self.right(xs, ys)) if callable(self.right) else self.right
-            return self._combine(left, right)
+        # one device program when the expression fits (<= 4 leaves); otherwise the backend builds the operands
+        # separately (each on the device when it can, a user-defined kernel through its own k) and combines them
+        # on the device (backend.cov)
+        return self._device_k(x, y)
 
     def __getstate__(self):
         right = self.right.__getstate__() if callable(self.right) else make_serializable(self.right)

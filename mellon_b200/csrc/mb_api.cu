@@ -554,6 +554,27 @@ extern "C" int mb_mat_scale(mb_ctx* c, mb_mat* a, double s) {
   return 0;
 }
 
+// a <- a (+ | *) b, a (+ | *) value, or a ** value, elementwise
+__global__ void k_combine(double* __restrict__ a, const double* __restrict__ b, int64_t n, int op, double value) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) {
+    const double x = a[i], y = b ? b[i] : value;
+    a[i] = (op == MB_OP_ADD) ? x + y : (op == MB_OP_MUL) ? x * y : pow(x, value);
+  }
+}
+
+extern "C" int mb_mat_combine(mb_ctx* c, int op, mb_mat* a, const mb_mat* b, double value) {
+  MB_CHECK(c && a, "mb_mat_combine: null argument");
+  MB_CHECK(op == MB_OP_ADD || op == MB_OP_MUL || op == MB_OP_POW, "mb_mat_combine: op %d is not ADD / MUL / POW", op);
+  MB_CHECK(!b || (op != MB_OP_POW && b->rows == a->rows && b->cols == a->cols), "mb_mat_combine: operand mismatch");
+  MB_CUDA(cudaSetDevice(c->device));
+  int64_t n = a->rows * a->cols;
+  if (n == 0) return 0;
+  int grid = (int)min((int64_t)c->n_sm * 8, ceil_div64(n, 256));
+  MB_LAUNCH(c, k_combine, grid, 256, 0, a->p, b ? b->p : nullptr, n, op, value);
+  return 0;
+}
+
 extern "C" int mb_mat_row_sumsq(mb_ctx* c, const mb_mat* a, mb_mat* out) {
   MB_CHECK(c && a && out, "mb_mat_row_sumsq: null argument");
   MB_CHECK(out->rows * out->cols == a->rows, "mb_mat_row_sumsq: output has %lld entries for %lld rows",

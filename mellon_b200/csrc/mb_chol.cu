@@ -85,8 +85,8 @@ int trsm_rec(mb_ctx* ctx, const double* Lp, int64_t ldl, int64_t c0, int64_t w, 
   int64_t w1 = ((w / 2 + NB - 1) / NB) * NB;
   MB_TRY(trsm_rec(ctx, Lp, ldl, c0, w1, X, ldx, nrows));
   // X[:, c0+w1 : c0+w] -= X[:, c0 : c0+w1] . Lp[c0+w1 : c0+w, c0 : c0+w1]^T
-  MB_TRY(mb_gemm_raw(ctx, false, false, nrows, w - w1, w1, -1.0, X + c0, ldx, Lp + (c0 + w1) * ldl + c0, ldl,
-                     1.0, X + c0 + w1, ldx, false));
+  MB_TRY(mb_gemm_rows_raw(ctx, false, false, nrows, w - w1, w1, -1.0, X + c0, ldx, Lp + (c0 + w1) * ldl + c0, ldl,
+                          1.0, X + c0 + w1, ldx));
   return trsm_rec(ctx, Lp, ldl, c0 + w1, w - w1, X, ldx, nrows);
 }
 
@@ -144,12 +144,12 @@ int trsm_inv_rec(mb_ctx* ctx, const double* Lp, int64_t ldl, const double* inv, 
   if (w <= IB) {
     // in place: a CTA consumes its whole 128 x w input tile before it stores the same tile
     const double* Tinv = inv + (c0 / IB) * IB * IB;
-    return mb_gemm_raw(ctx, false, false, nrows, w, w, 1.0, X + c0, ldx, Tinv, IB, 0.0, X + c0, ldx, false);
+    return mb_gemm_rows_raw(ctx, false, false, nrows, w, w, 1.0, X + c0, ldx, Tinv, IB, 0.0, X + c0, ldx);
   }
   const int64_t w1 = ((w / 2 + IB - 1) / IB) * IB;
   MB_TRY(trsm_inv_rec(ctx, Lp, ldl, inv, c0, w1, X, ldx, nrows));
-  MB_TRY(mb_gemm_raw(ctx, false, false, nrows, w - w1, w1, -1.0, X + c0, ldx, Lp + (c0 + w1) * ldl + c0, ldl, 1.0,
-                     X + c0 + w1, ldx, false));
+  MB_TRY(mb_gemm_rows_raw(ctx, false, false, nrows, w - w1, w1, -1.0, X + c0, ldx, Lp + (c0 + w1) * ldl + c0, ldl, 1.0,
+                          X + c0 + w1, ldx));
   return trsm_inv_rec(ctx, Lp, ldl, inv, c0 + w1, w - w1, X, ldx, nrows);
 }
 
@@ -571,9 +571,10 @@ trsv_update_bwd_kernel(const double* __restrict__ L, int64_t ldl, int64_t row0, 
 }  // namespace
 
 int mb_trsm_right_lt_raw(mb_ctx* ctx, const double* Lp, int64_t ldl, int64_t m, double* X, int64_t ldx,
-                         int64_t nrows) {
+                         int64_t nrows, int64_t rows_total) {
   if (nrows <= 0 || m <= 0) return 0;
-  if (ctx->opt_trsm == 1 || nrows < 4 * IB) return trsm_rec(ctx, Lp, ldl, 0, m, X, ldx, nrows);
+  // the algorithm is chosen from the GLOBAL row count, so a row's result does not depend on how the cells are sharded
+  if (ctx->opt_trsm == 1 || std::max(nrows, rows_total) < 4 * IB) return trsm_rec(ctx, Lp, ldl, 0, m, X, ldx, nrows);
   // tall right-hand sides: every flop in the DMMA GEMM (diagonal blocks applied as explicit 128 x 128 inverses)
   const int64_t nb = ceil_div64(m, IB);
   MB_TRY(mb_trsm_ws(ctx, m));
@@ -686,7 +687,8 @@ extern "C" int mb_trsm_right_lt(mb_ctx* ctx, const mb_mat* Lp, mb_mat* X) {
            "mb_trsm_right_lt: Lp is %lld x %lld, X is %lld x %lld", (long long)Lp->rows,
            (long long)Lp->cols, (long long)X->rows, (long long)X->cols);
   MB_CUDA(cudaSetDevice(ctx->device));
-  return mb_trsm_right_lt_raw(ctx, Lp->p, Lp->cols, Lp->rows, X->p, X->cols, X->rows);
+  return mb_trsm_right_lt_raw(ctx, Lp->p, Lp->cols, Lp->rows, X->p, X->cols, X->rows,
+                              X->global_rows >= 0 ? X->global_rows : X->rows);
 }
 
 extern "C" int mb_tri_solve(mb_ctx* ctx, const mb_mat* Lp, int trans, mb_mat* B) {

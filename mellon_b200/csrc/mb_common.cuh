@@ -18,7 +18,40 @@ struct mb_mat {
   mb_ctx* ctx;
   bool owns;
   size_t alloc_bytes = 0;  // size of the device block behind p (>= rows * cols * 8 when it came from the cache)
+  // row block [row_lo, row_lo + rows) of a matrix of `global_rows` rows whose cell axis is sharded over the ranks
+  // (mb_mat_set_shard); -1 = not sharded: reductions over its rows stay on this rank
+  int64_t global_rows = -1;
+  int64_t row_lo = 0;
 };
+
+// ---- fixed reduction tree over the cell axis ------------------------------------------------------------------
+// Every sum over cells (Gram, L^T t, loss + gradient, Hessian diagonal) is formed the same way whatever the number
+// of ranks: the GLOBAL cell axis is cut into MB_NCHUNK chunks of ceil(G / MB_NCHUNK) rows, each chunk is summed in
+// an order that depends on the chunk alone, and the chunk sums are combined by one pairwise tree over the chunk
+// index.  Rank boundaries fall on chunk boundaries (backend.row_block), so a rank owns a contiguous range of leaves.
+constexpr int MB_NCHUNK = 32;
+struct mb_chunks {
+  int64_t G;        // global rows
+  int64_t cr;       // rows per chunk
+  int64_t row_lo;   // first global row held locally
+  int64_t rows;     // local rows
+  int c_lo, c_hi;   // local chunk range [c_lo, c_hi) in global chunk ids
+  bool sharded;     // combine across ranks
+  // local row range of global chunk c (empty when c lies beyond G)
+  inline void range(int c, int64_t* i0, int64_t* i1) const {
+    int64_t a = std::min<int64_t>(G, (int64_t)c * cr), b = std::min<int64_t>(G, (int64_t)(c + 1) * cr);
+    *i0 = a - row_lo;
+    *i1 = b - row_lo;
+  }
+};
+int mb_chunk_grid(mb_ctx* ctx, const mb_mat* m, mb_chunks* out);
+// leaves: MB_NCHUNK x count doubles (global chunk slots; the producer writes exact zeros into the slots this rank
+// does not own); out <- tree sum over all chunks of all ranks (all-reduce of the zero-padded leaves when sharded)
+int mb_tree_reduce_small(mb_ctx* ctx, const mb_chunks& g, double* leaves, int64_t count, double* out);
+// tree over matrices too large to gather: `acc` holds this rank's tree sum of its own leaves on entry and the global
+// tree sum on return (butterfly exchange for power-of-two worlds whose ranks own aligned subtrees)
+int mb_tree_combine_ranks(mb_ctx* ctx, const mb_chunks& g, double* acc, int64_t count);
+int mb_axpy_raw(mb_ctx* ctx, double* dst, const double* src, int64_t count);  // dst = dst + src (elementwise)
 
 // kernel classes for the in-library stopwatch (mb_prof_*): CUDA events around each launch
 enum { MB_PROF_COV = 0, MB_PROF_MATVEC = 1, MB_PROF_GEMM = 2, MB_PROF_LOSSGRAD = 3, MB_PROF_OTHER = 4,
@@ -150,11 +183,24 @@ int mb_mat_view(mb_ctx* ctx, double* p, int64_t rows, int64_t cols, mb_mat* out)
 int mb_gemm_raw(mb_ctx* ctx, bool a_kmajor, bool b_kmajor, int64_t m, int64_t n, int64_t k,
                 double alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
                 double beta, double* C, int64_t ldc, bool lower_only);
+// same for products whose output rows are cells (m = local cells): never split along k, so that an output row does
+// not depend on how many rows this rank happens to hold
+int mb_gemm_rows_raw(mb_ctx* ctx, bool a_kmajor, bool b_kmajor, int64_t m, int64_t n, int64_t k,
+                     double alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
+                     double beta, double* C, int64_t ldc);
+// C (m x n) = A^T B summed over the rows (cells) of A (k x m) and B (k x n) through the fixed chunk tree of `g`;
+// lower_only: A == B, lower tiles + mirror.  The result is the GLOBAL sum on every rank when g.sharded.
+int mb_gemm_tn_cells(mb_ctx* ctx, const mb_chunks& g, int64_t m, int64_t n, const double* A, int64_t lda,
+                     const double* B, int64_t ldb, double* C, int64_t ldc, bool lower_only);
 
 int mb_potrf_raw(mb_ctx* ctx, double* A, int64_t n, int64_t lda, int* info_dev_accum);
 int mb_trsm_right_lt_raw(mb_ctx* ctx, const double* Lp, int64_t ldl, int64_t m, double* X,
-                         int64_t ldx, int64_t nrows);
+                         int64_t ldx, int64_t nrows, int64_t rows_total);
 int mb_allreduce_raw(mb_ctx* ctx, double* p, int64_t count);
+// exchange `count` doubles with rank `peer` (ncclSend + ncclRecv in one group) on the context's stream
+int mb_sendrecv_raw(mb_ctx* ctx, const double* send, double* recv, int64_t count, int peer);
+// broadcast `count` doubles from rank `root`
+int mb_bcast_raw(mb_ctx* ctx, double* p, int64_t count, int root);
 void mb_invalidate_graphs(mb_ctx* ctx);  // captured graphs hold raw workspace pointers: drop them when one moves
 int mb_gemm_reserve_ws(mb_ctx* ctx, size_t bytes);  // grow the split-k workspace up front (no cudaMalloc under capture)
 

@@ -367,7 +367,8 @@ __global__ void splitk_reduce_kernel(const double* __restrict__ ws, int ksplit, 
 
 template <bool AK, bool BK>
 int launch_gemm(mb_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
-                const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only) {
+                const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only,
+                bool allow_split = true) {
   if (ctx->opt_gemm == 1) {
     int64_t tm = ceil_div64(m, 64), tn = ceil_div64(n, 64), nt = tm * tn;
     int grid = (int)min(nt, (int64_t)ctx->n_sm * 8);
@@ -388,7 +389,7 @@ int launch_gemm(mb_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, cons
   // split the contraction axis when the tile count leaves the last wave of CTAs mostly idle: few tiles (the
   // mid-size products inside the Cholesky) split down to 512-deep chunks, many tiles only to 4096-deep ones
   int ksplit = 1;
-  if (ctx->opt_gemm != 3) {
+  if (ctx->opt_gemm != 3 && allow_split) {
     const int64_t sm = ctx->n_sm;
     const int64_t min_chunk = (nt < 4 * sm) ? 512 : 4096;
     double best = (double)nt / (double)(ceil_div64(nt, sm) * sm);
@@ -458,6 +459,19 @@ int mb_gemm_raw(mb_ctx* ctx, bool a_kmajor, bool b_kmajor, int64_t m, int64_t n,
   return launch_gemm<false, false>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only);
 }
 
+int mb_gemm_rows_raw(mb_ctx* ctx, bool a_kmajor, bool b_kmajor, int64_t m, int64_t n, int64_t k, double alpha,
+                     const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
+                     int64_t ldc) {
+  if (m <= 0 || n <= 0) return 0;
+  MB_CUDA(cudaSetDevice(ctx->device));
+  if (a_kmajor) {
+    if (b_kmajor) return launch_gemm<true, true>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, false, false);
+    return launch_gemm<true, false>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, false, false);
+  }
+  if (b_kmajor) return launch_gemm<false, true>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, false, false);
+  return launch_gemm<false, false>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, false, false);
+}
+
 // C = alpha op(A) op(B) + beta C with row-major matrices.
 //   op(A) (m x k): trans_a=0 -> A is m x k (A(i,k)=A[i*lda+k], not k-major); trans_a=1 -> A is k x m (k-major)
 //   op(B) (k x n): trans_b=0 -> B is k x n (B(j,k)=B[k*ldb+j], k-major);     trans_b=1 -> B is n x k (not k-major)
@@ -469,9 +483,19 @@ extern "C" int mb_gemm(mb_ctx* ctx, int trans_a, int trans_b, double alpha, cons
   MB_CHECK(ka == kb, "mb_gemm: inner dimensions differ (%lld vs %lld)", (long long)ka, (long long)kb);
   MB_CHECK(C->rows == m && C->cols == n, "mb_gemm: output is %lld x %lld, expected %lld x %lld",
            (long long)C->rows, (long long)C->cols, (long long)m, (long long)n);
+  if (trans_a && !trans_b && A->global_rows >= 0) {
+    // contraction over the cell axis of a sharded operand: fixed chunk tree, summed over all ranks
+    MB_CHECK(alpha == 1.0 && beta == 0.0, "mb_gemm: a product contracted over sharded cells takes alpha = 1, beta = 0");
+    MB_CHECK(B->global_rows == A->global_rows && B->row_lo == A->row_lo, "mb_gemm: operands are sharded differently");
+    mb_chunks g;
+    MB_TRY(mb_chunk_grid(ctx, A, &g));
+    return mb_gemm_tn_cells(ctx, g, m, n, A->p, A->cols, B->p, B->cols, C->p, C->cols, false);
+  }
   if (ka == 0) {
     if (beta == 0.0) return mb_mat_fill(ctx, C, 0.0);
   }
+  if (!trans_a && A->global_rows >= 0)  // output rows are cells: an output row must not depend on the local row count
+    return mb_gemm_rows_raw(ctx, false, trans_b == 0, m, n, ka, alpha, A->p, A->cols, B->p, B->cols, beta, C->p, C->cols);
   return mb_gemm_raw(ctx, trans_a != 0, trans_b == 0, m, n, ka, alpha, A->p, A->cols, B->p, B->cols, beta, C->p,
                      C->cols, false);
 }

@@ -9,22 +9,51 @@ namespace {
 constexpr int ROW_THREADS = 256;   // 8 warps per CTA, one row per warp at a time
 enum { MODE_TRANSFORM = 0, MODE_GRAD = 1, MODE_HESS = 2 };
 
+// Segments: the unit of work of every pass that sums over cells.  A segment is a run of `sr` consecutive GLOBAL rows
+// inside one chunk of the fixed reduction tree (mb_common.cuh); its rows are summed in row order by one CTA, the
+// `spc` segment sums of a chunk are added in segment order, and the chunk sums go through the pairwise tree.  None of
+// this depends on which rank holds the rows, so the bits of the result do not depend on the number of ranks.
+constexpr int SEG_PER_CHUNK = 37;   // 32 chunks x 37 = 1184 = 8 x 148 SMs: whole waves on 1, 2, 4 and 8 ranks
+constexpr int SEG_MIN_ROWS = 16;
+struct SegGrid {
+  int64_t cr, sr, G, row_lo;
+  int spc, c_lo, c_hi, nseg;
+};
+SegGrid make_seg_grid(const mb_chunks& g) {
+  SegGrid s;
+  s.cr = g.cr;
+  s.G = g.G;
+  s.row_lo = g.row_lo;
+  s.sr = std::max<int64_t>(SEG_MIN_ROWS, ceil_div64(g.cr, SEG_PER_CHUNK));
+  s.spc = (int)ceil_div64(g.cr, s.sr);
+  s.c_lo = g.c_lo;
+  s.c_hi = g.c_hi;
+  s.nseg = (g.c_hi - g.c_lo) * s.spc;
+  return s;
+}
+// local row range [i0, i1) of local segment `seg` (possibly empty)
+__device__ __forceinline__ void seg_rows(const SegGrid& s, int seg, int64_t* i0, int64_t* i1) {
+  const int c = s.c_lo + seg / s.spc, j = seg % s.spc;
+  const int64_t cend = min(s.G, (int64_t)(c + 1) * s.cr);
+  const int64_t a = min(cend, (int64_t)c * s.cr + (int64_t)j * s.sr), b = min(cend, a + s.sr);
+  *i0 = a - s.row_lo;
+  *i1 = b - s.row_lo;
+}
+
 // f_i = L[i,:] . z + mu ; per mode:
 //   TRANSFORM: out_f[i] = f_i
-//   GRAD:      wv[i] = exp(f_i + V_i) - 1 ; partial[block] = sum (f_i - A_i)
+//   GRAD:      wv[i] = exp(f_i + V_i) - 1 ; lv[i] = f_i - A_i
 //   HESS:      wv[i] = exp(f_i + V_i)
 template <int MODE>
 __global__ void __launch_bounds__(ROW_THREADS)
 rowdot_kernel(const double* __restrict__ L, int64_t n, int r, const double* __restrict__ z, double mu,
-              const double* __restrict__ V, double* __restrict__ out, double* __restrict__ partial) {
+              const double* __restrict__ V, double* __restrict__ out, double* __restrict__ lv) {
   extern __shared__ double zs[];
-  __shared__ double red[ROW_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int c = tid; c < r; c += ROW_THREADS) zs[c] = z[c];
   __syncthreads();
   const int64_t warps_total = (int64_t)gridDim.x * (ROW_THREADS / 32);
   const bool vec = ((r & 1) == 0) && ((reinterpret_cast<uintptr_t>(L) & 15) == 0);
-  double local = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * (ROW_THREADS / 32) + warp; i < n; i += warps_total) {
     const double* row = L + i * r;
     double s0 = 0.0, s1 = 0.0;
@@ -54,29 +83,33 @@ rowdot_kernel(const double* __restrict__ L, int64_t n, int r, const double* __re
       } else {
         double A = exp(f + V[i]);
         out[i] = (MODE == MODE_GRAD) ? (A - 1.0) : A;
-        if (MODE == MODE_GRAD) local += f - A;
+        if (MODE == MODE_GRAD) lv[i] = f - A;
       }
-    }
-  }
-  if (MODE == MODE_GRAD) {
-    if (lane == 0) red[warp] = local;
-    __syncthreads();
-    if (tid == 0) {
-      double s = 0.0;
-      for (int w = 0; w < ROW_THREADS / 32; w++) s += red[w];
-      partial[blockIdx.x] = s;
     }
   }
 }
 
-// partial[chunk][c] = sum_{i in chunk} wv[i] * (SQ ? L[i,c]^2 : L[i,c])
+// lpartial[seg] = sum of lv over the rows of the segment: one warp per segment, lane-strided then a shuffle tree
+__global__ void __launch_bounds__(256)
+seg_sum_kernel(const double* __restrict__ lv, const SegGrid sg, double* __restrict__ lpartial) {
+  const int seg = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (seg >= sg.nseg) return;
+  int64_t i0, i1;
+  seg_rows(sg, seg, &i0, &i1);
+  double s = 0.0;
+  for (int64_t i = i0 + lane; i < i1; i += 32) s += lv[i];
+  s = warp_sum(s);
+  if (lane == 0) lpartial[seg] = s;
+}
+
+// partial[seg][c] = sum_{i in segment} wv[i] * (SQ ? L[i,c]^2 : L[i,c])
 template <bool SQ>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const double* __restrict__ L, int64_t n, int r, const double* __restrict__ wv,
-              int64_t rows_per_chunk, double* __restrict__ partial) {
+              const SegGrid sg, double* __restrict__ partial) {
   const int c = (blockIdx.x * 256 + threadIdx.x) * 2;
-  const int64_t i0 = (int64_t)blockIdx.y * rows_per_chunk;
-  const int64_t i1 = min(n, i0 + rows_per_chunk);
+  int64_t i0, i1;
+  seg_rows(sg, blockIdx.y, &i0, &i1);
   if (c >= r) return;
   const bool pair = (c + 1 < r);
   const bool vec = pair && ((r & 1) == 0) && ((reinterpret_cast<uintptr_t>(L) & 15) == 0);
@@ -111,18 +144,39 @@ colsum_kernel(const double* __restrict__ L, int64_t n, int r, const double* __re
   if (pair) p[c + 1] = a1 + b1;
 }
 
-// out[c] = sum_chunk partial[chunk][c]  (fixed order) ; out[r] = sum_b lpartial[b] when n_lp > 0
-__global__ void reduce_chunks_kernel(const double* __restrict__ partial, int n_chunks, int r,
-                                     const double* __restrict__ lpartial, int n_lp, double* __restrict__ out) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < r) {
+// leaves[c][j] = sum over the segments of chunk c, in segment order, of partial[seg][j]  (j < r), and of
+// lpartial[seg] for j == r when has_l; chunks this rank does not hold get an exact zero.  FUSE (one rank): the
+// pairwise tree over the chunk sums is taken right here and out[j] written instead.
+template <bool FUSE>
+__global__ void seg_reduce_kernel(const double* __restrict__ partial, const double* __restrict__ lpartial, int r,
+                                  int has_l, const SegGrid sg, double* __restrict__ dst) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int count = r + (has_l ? 1 : 0);
+  if (j >= count) return;
+  double v[MB_NCHUNK];
+#pragma unroll
+  for (int c = 0; c < MB_NCHUNK; c++) {
     double s = 0.0;
-    for (int k = 0; k < n_chunks; k++) s += partial[(int64_t)k * r + c];
-    out[c] = s;
-  } else if (c == r && n_lp > 0) {
-    double s = 0.0;
-    for (int k = 0; k < n_lp; k++) s += lpartial[k];
-    out[r] = s;
+    if (c >= sg.c_lo && c < sg.c_hi) {
+      const int s0 = (c - sg.c_lo) * sg.spc;
+      if (j < r) {
+        for (int q = 0; q < sg.spc; q++) s += partial[(int64_t)(s0 + q) * r + j];
+      } else {
+        for (int q = 0; q < sg.spc; q++) s += lpartial[s0 + q];
+      }
+    }
+    v[c] = s;
+  }
+  if (FUSE) {
+#pragma unroll
+    for (int w = MB_NCHUNK / 2; w >= 1; w >>= 1) {
+#pragma unroll
+      for (int i = 0; i < w; i++) v[i] = v[2 * i] + v[2 * i + 1];
+    }
+    dst[j] = v[0];
+  } else {
+#pragma unroll
+    for (int c = 0; c < MB_NCHUNK; c++) dst[(int64_t)c * count + j] = v[c];
   }
 }
 
@@ -134,14 +188,14 @@ __global__ void reduce_chunks_kernel(const double* __restrict__ partial, int n_c
 template <int CP, int RG, bool SQ>
 __global__ void __launch_bounds__(512, 1)
 fused_rows_kernel(const double* __restrict__ L, int64_t n, int r, const double* __restrict__ z, double mu,
-                  const double* __restrict__ V, int64_t rows_per_cta, double* __restrict__ partial,
+                  const double* __restrict__ V, const SegGrid sg, double* __restrict__ partial,
                   double* __restrict__ lpartial) {
   constexpr int T = 512, NW = T / 32;
   __shared__ double red[2][RG][NW];
   __shared__ double fsh[2][RG];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t i0 = (int64_t)blockIdx.x * rows_per_cta;
-  const int64_t i1 = min(n, i0 + rows_per_cta);
+  int64_t i0, i1;
+  seg_rows(sg, blockIdx.x, &i0, &i1);
 
   double2 zr[CP], g[CP];
 #pragma unroll
@@ -275,7 +329,7 @@ __device__ __forceinline__ void s_mbar_arrive(uint64_t* bar) {
 template <int CP, bool SQ, bool HOLD>
 __global__ void __launch_bounds__(ST_ALL, 1)
 stream_rows_kernel(const double* __restrict__ L, int64_t n, int r, const double* __restrict__ z, double mu,
-                   const double* __restrict__ V, int64_t rows_per_cta, int rb, int ns,
+                   const double* __restrict__ V, const SegGrid sg, int rb, int ns,
                    double* __restrict__ partial, double* __restrict__ lpartial) {
   extern __shared__ __align__(128) unsigned char stream_smem[];
   double* ring = reinterpret_cast<double*>(stream_smem);
@@ -283,8 +337,8 @@ stream_rows_kernel(const double* __restrict__ L, int64_t n, int r, const double*
   __shared__ double red[2][SMAX_RB][SRED];
   __shared__ double wsh[2][SMAX_RB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t i0 = (int64_t)blockIdx.x * rows_per_cta;
-  const int64_t i1 = min(n, i0 + rows_per_cta);
+  int64_t i0, i1;
+  seg_rows(sg, blockIdx.x, &i0, &i1);
   const int64_t nslab = (i1 > i0) ? (i1 - i0 + rb - 1) / rb : 0;
   const size_t stage_doubles = (size_t)rb * r;
 
@@ -462,27 +516,44 @@ stream_rows_kernel(const double* __restrict__ L, int64_t n, int r, const double*
 
 struct PassBuffers {
   double* zdev;      // r
-  double* wv;        // n
-  double* partial;   // chunks * r
-  double* lpartial;  // up to 4096
+  double* wv;        // n   (two-pass route: per-row weights)
+  double* lv;        // n   (two-pass route: per-row loss terms)
+  double* partial;   // nseg * r
+  double* lpartial;  // nseg
+  double* leaves;    // MB_NCHUNK * (r + 1)
   double* out;       // r + 1
 };
 
-int carve(mb_ctx* ctx, int64_t n, int r, int64_t chunks, PassBuffers* pb) {
-  size_t need = ((size_t)r + (size_t)n + (size_t)chunks * r + 4096 + (size_t)r + 8) * sizeof(double);
+int carve(mb_ctx* ctx, int64_t n, int r, int64_t nseg, PassBuffers* pb) {
+  const size_t rp = (size_t)r + 2, np = (size_t)n + 2, sp = (size_t)nseg + 2;
+  size_t need = (rp + 2 * np + (size_t)nseg * r + sp + (size_t)MB_NCHUNK * rp + rp + 8) * sizeof(double);
   double* s;
   MB_TRY(mb_scratch(ctx, need, &s));
   pb->zdev = s;
-  pb->wv = pb->zdev + r + (r & 1);
-  pb->partial = pb->wv + n + (n & 1);
-  pb->lpartial = pb->partial + chunks * r;
-  pb->out = pb->lpartial + 4096;
+  pb->wv = pb->zdev + (rp & ~(size_t)1);
+  pb->lv = pb->wv + (np & ~(size_t)1);
+  pb->partial = pb->lv + (np & ~(size_t)1);
+  pb->lpartial = pb->partial + (size_t)nseg * r + ((size_t)nseg * r & 1);
+  pb->leaves = pb->lpartial + (sp & ~(size_t)1);
+  pb->out = pb->leaves + (size_t)MB_NCHUNK * rp;
   return 0;
+}
+
+// segment partials -> chunk leaves -> tree -> pb->out (count = r, + 1 when the loss slot is carried)
+int finish_reduce(mb_ctx* ctx, const mb_chunks& g, const SegGrid& sg, int r, bool has_l, PassBuffers* pb) {
+  const int count = r + (has_l ? 1 : 0);
+  const int grid = (int)ceil_div64(count, 128);
+  if (!g.sharded) {
+    MB_LAUNCH(ctx, seg_reduce_kernel<true>, grid, 128, 0, pb->partial, pb->lpartial, r, has_l ? 1 : 0, sg, pb->out);
+    return 0;
+  }
+  MB_LAUNCH(ctx, seg_reduce_kernel<false>, grid, 128, 0, pb->partial, pb->lpartial, r, has_l ? 1 : 0, sg, pb->leaves);
+  return mb_tree_reduce_small(ctx, g, pb->leaves, count, pb->out);
 }
 
 template <int MODE>
 int launch_rowdot(mb_ctx* ctx, const mb_mat* L, const double* zdev, double mu, const double* V, double* out,
-                  double* partial, int* nblocks) {
+                  double* lv) {
   int grid = (int)min((int64_t)ctx->n_sm * 4, ceil_div64(L->rows, ROW_THREADS / 32));
   grid = max(grid, 1);
   size_t smem = (size_t)L->cols * sizeof(double);
@@ -492,50 +563,34 @@ int launch_rowdot(mb_ctx* ctx, const mb_mat* L, const double* zdev, double mu, c
     MB_CUDA(cudaFuncSetAttribute(rowdot_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     configured[MODE] = true;
   }
-  MB_LAUNCH(ctx, rowdot_kernel<MODE>, grid, ROW_THREADS, smem, L->p, L->rows, (int)L->cols, zdev, mu, V, out,
-            partial);
-  if (nblocks) *nblocks = grid;
+  MB_LAUNCH(ctx, rowdot_kernel<MODE>, grid, ROW_THREADS, smem, L->p, L->rows, (int)L->cols, zdev, mu, V, out, lv);
   return 0;
 }
 
-// two-pass route: (A-1 | A | t) weights in wv, then column sums
-int colsum(mb_ctx* ctx, const mb_mat* L, const double* wv, bool sq, PassBuffers* pb, int64_t chunks,
-           const double* lpartial, int n_lp) {
+// two-pass route: (A-1 | A | t) weights in wv, then column sums per segment (+ the per-row loss terms in lv)
+int colsum(mb_ctx* ctx, const mb_mat* L, const double* wv, bool sq, PassBuffers* pb, const SegGrid& sg, const double* lv) {
   const int r = (int)L->cols;
-  int64_t rows_per_chunk = ceil_div64(L->rows, chunks);
-  dim3 grid((unsigned)ceil_div64(r, 512), (unsigned)chunks);
-  if (sq) MB_LAUNCH(ctx, colsum_kernel<true>, grid, 256, 0, L->p, L->rows, r, wv, rows_per_chunk, pb->partial);
-  else MB_LAUNCH(ctx, colsum_kernel<false>, grid, 256, 0, L->p, L->rows, r, wv, rows_per_chunk, pb->partial);
-  MB_LAUNCH(ctx, reduce_chunks_kernel, (int)ceil_div64(r + 1, 256), 256, 0, pb->partial, (int)chunks, r, lpartial,
-            n_lp, pb->out);
+  if (sg.nseg == 0) return 0;
+  dim3 grid((unsigned)ceil_div64(r, 512), (unsigned)sg.nseg);
+  if (sq) MB_LAUNCH(ctx, colsum_kernel<true>, grid, 256, 0, L->p, L->rows, r, wv, sg, pb->partial);
+  else MB_LAUNCH(ctx, colsum_kernel<false>, grid, 256, 0, L->p, L->rows, r, wv, sg, pb->partial);
+  if (lv) MB_LAUNCH(ctx, seg_sum_kernel, (int)ceil_div64(sg.nseg, 8), 256, 0, lv, sg, pb->lpartial);
   return 0;
-}
-
-int64_t pick_chunks(mb_ctx* ctx, int64_t n, int r) {
-  int64_t col_blocks = ceil_div64(r, 512);
-  int64_t chunks = ceil_div64((int64_t)ctx->n_sm * 4, col_blocks);
-  chunks = min(chunks, ceil_div64(n, 64));
-  return std::max<int64_t>(chunks, 1);
 }
 
 template <bool SQ>
 int launch_fused(mb_ctx* ctx, const mb_mat* L, const double* zdev, double mu, const double* V, PassBuffers* pb,
-                 int64_t n_cta, bool* done) {
+                 const SegGrid& sg, bool* done) {
   const int r = (int)L->cols;
   const int64_t n = L->rows;
   *done = false;
   if ((r & 1) || (reinterpret_cast<uintptr_t>(L->p) & 15)) return 0;
   const int cp = (int)ceil_div64(r, 1024);
-  int64_t rows_per_cta = ceil_div64(n, n_cta);
 #define MB_FUSED(CPV, RGV)                                                                                \
   {                                                                                                       \
-    rows_per_cta = ceil_div64(rows_per_cta, RGV) * RGV;                                                   \
-    int grid = (int)ceil_div64(n, rows_per_cta);                                                          \
     if (ctx->prof_on) ctx->prof_work[MB_PROF_LOSSGRAD] += 8.0 * ((double)n * r + (double)n);                \
-    MB_LAUNCH_P(ctx, MB_PROF_LOSSGRAD, (fused_rows_kernel<CPV, RGV, SQ>), grid, 512, 0, L->p, n, r, zdev, mu, V, rows_per_cta, \
+    MB_LAUNCH_P(ctx, MB_PROF_LOSSGRAD, (fused_rows_kernel<CPV, RGV, SQ>), sg.nseg, 512, 0, L->p, n, r, zdev, mu, V, sg, \
               pb->partial, pb->lpartial);                                                                 \
-    MB_LAUNCH(ctx, reduce_chunks_kernel, (int)ceil_div64(r + 1, 256), 256, 0, pb->partial, grid, r,       \
-              pb->lpartial, SQ ? 0 : grid, pb->out);                                                      \
     *done = true;                                                                                         \
   }
   if (cp == 1) MB_FUSED(1, 8)
@@ -552,7 +607,7 @@ int launch_fused(mb_ctx* ctx, const mb_mat* L, const double* zdev, double mu, co
 
 template <bool SQ>
 int launch_stream(mb_ctx* ctx, const mb_mat* L, const double* zdev, double mu, const double* V, PassBuffers* pb,
-                  int64_t n_cta, bool* done) {
+                  const SegGrid& sg, bool* done) {
   const int r = (int)L->cols;
   const int64_t n = L->rows;
   *done = false;
@@ -564,8 +619,7 @@ int launch_stream(mb_ctx* ctx, const mb_mat* L, const double* zdev, double mu, c
   const size_t budget = 200 * 1024;
   int ns = (int)std::min<size_t>(SMAX_NS, budget / stage);
   if (ns < 3) return 0;
-  int64_t rows_per_cta = ceil_div64(ceil_div64(n, n_cta), rb) * rb;
-  const int grid = (int)ceil_div64(n, rows_per_cta);
+  const int grid = sg.nseg;
   const size_t smem = (size_t)ns * stage;
   const int cp = (int)ceil_div64(r, 2 * ST);
   const bool hold = (rb == 1 && cp <= 6);  // row copy in registers: 4 * cp more registers
@@ -582,10 +636,10 @@ int launch_stream(mb_ctx* ctx, const mb_mat* L, const double* zdev, double mu, c
     if (ctx->prof_on) ctx->prof_work[MB_PROF_LOSSGRAD] += 8.0 * ((double)n * r + (double)n);                \
     if (hold) {                                                                                             \
       MB_LAUNCH_P(ctx, MB_PROF_LOSSGRAD, (stream_rows_kernel<CPV, SQ, true>), grid, ST_ALL, smem, L->p, n, r, zdev, mu, \
-                  V, rows_per_cta, rb, ns, pb->partial, pb->lpartial);                                      \
+                  V, sg, rb, ns, pb->partial, pb->lpartial);                                                \
     } else {                                                                                                \
       MB_LAUNCH_P(ctx, MB_PROF_LOSSGRAD, (stream_rows_kernel<CPV, SQ, false>), grid, ST_ALL, smem, L->p, n, r, zdev, mu, \
-                  V, rows_per_cta, rb, ns, pb->partial, pb->lpartial);                                      \
+                  V, sg, rb, ns, pb->partial, pb->lpartial);                                                \
     }                                                                                                       \
     break;                                                                                                  \
   }
@@ -595,10 +649,31 @@ int launch_stream(mb_ctx* ctx, const mb_mat* L, const double* zdev, double mu, c
     default: return 0;
   }
 #undef MB_STREAM
-  MB_LAUNCH(ctx, reduce_chunks_kernel, (int)ceil_div64(r + 1, 256), 256, 0, pb->partial, grid, r, pb->lpartial,
-            SQ ? 0 : grid, pb->out);
   *done = true;
   return 0;
+}
+
+// one pass over the local rows of L with weights exp(f + V) [- 1]: gradient / Hessian-diagonal sums (and the loss
+// terms) per segment, then the fixed tree; the result (r [+ 1] doubles) is in pb->out on every rank
+template <bool SQ>
+int objective_pass(mb_ctx* ctx, const mb_mat* L, const mb_mat* V, double mu, const double* z_host, PassBuffers* pb) {
+  const int64_t n = L->rows;
+  const int r = (int)L->cols;
+  mb_chunks g;
+  MB_TRY(mb_chunk_grid(ctx, L, &g));
+  const SegGrid sg = make_seg_grid(g);
+  MB_TRY(carve(ctx, n, r, sg.nseg, pb));
+  MB_CUDA(cudaMemcpyAsync(pb->zdev, z_host, (size_t)r * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (sg.nseg > 0) {
+    bool done = false;
+    if (ctx->opt_lossgrad == 0) MB_TRY(launch_stream<SQ>(ctx, L, pb->zdev, mu, V->p, pb, sg, &done));
+    if (!done && ctx->opt_lossgrad != 1) MB_TRY(launch_fused<SQ>(ctx, L, pb->zdev, mu, V->p, pb, sg, &done));
+    if (!done) {
+      if (n > 0) MB_TRY((launch_rowdot<SQ ? MODE_HESS : MODE_GRAD>(ctx, L, pb->zdev, mu, V->p, pb->wv, pb->lv)));
+      MB_TRY(colsum(ctx, L, pb->wv, SQ, pb, sg, SQ ? nullptr : pb->lv));
+    }
+  }
+  return finish_reduce(ctx, g, sg, r, !SQ, pb);
 }
 
 }  // namespace
@@ -612,7 +687,7 @@ extern "C" int mb_transform(mb_ctx* ctx, const mb_mat* L, const double* z_host, 
   PassBuffers pb;
   MB_TRY(carve(ctx, n, r, 1, &pb));
   MB_CUDA(cudaMemcpyAsync(pb.zdev, z_host, (size_t)r * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  MB_TRY(launch_rowdot<MODE_TRANSFORM>(ctx, L, pb.zdev, mu, nullptr, pb.wv, nullptr, nullptr));
+  MB_TRY(launch_rowdot<MODE_TRANSFORM>(ctx, L, pb.zdev, mu, nullptr, pb.wv, nullptr));
   MB_CUDA(cudaMemcpyAsync(f_host, pb.wv, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   MB_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -624,26 +699,9 @@ extern "C" int mb_loss_grad(mb_ctx* ctx, const mb_mat* L, const mb_mat* V, doubl
   MB_CHECK(V->rows * V->cols == L->rows, "mb_loss_grad: V has %lld entries for %lld cells",
            (long long)(V->rows * V->cols), (long long)L->rows);
   MB_CUDA(cudaSetDevice(ctx->device));
-  const int64_t n = L->rows;
   const int r = (int)L->cols;
-  const int64_t n_cta = std::max<int64_t>(1, min((int64_t)ctx->n_sm, ceil_div64(n, 8)));
-  const int64_t chunks = max(pick_chunks(ctx, n, r), n_cta);
   PassBuffers pb;
-  MB_TRY(carve(ctx, n, r, chunks, &pb));
-  MB_CUDA(cudaMemcpyAsync(pb.zdev, z_host, (size_t)r * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  if (n == 0) {
-    MB_CUDA(cudaMemsetAsync(pb.out, 0, (size_t)(r + 1) * sizeof(double), ctx->stream));
-  } else {
-    bool done = false;
-    if (ctx->opt_lossgrad == 0) MB_TRY(launch_stream<false>(ctx, L, pb.zdev, mu, V->p, &pb, n_cta, &done));
-    if (!done && ctx->opt_lossgrad != 1) MB_TRY(launch_fused<false>(ctx, L, pb.zdev, mu, V->p, &pb, n_cta, &done));
-    if (!done) {
-      int nb = 0;
-      MB_TRY(launch_rowdot<MODE_GRAD>(ctx, L, pb.zdev, mu, V->p, pb.wv, pb.lpartial, &nb));
-      MB_TRY(colsum(ctx, L, pb.wv, false, &pb, pick_chunks(ctx, n, r), pb.lpartial, nb));
-    }
-  }
-  MB_TRY(mb_allreduce_raw(ctx, pb.out, r + 1));
+  MB_TRY(objective_pass<false>(ctx, L, V, mu, z_host, &pb));
   double* host;
   MB_TRY(mb_pinned(ctx, (size_t)(r + 1) * sizeof(double), &host));
   MB_CUDA(cudaMemcpyAsync(host, pb.out, (size_t)(r + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -664,25 +722,9 @@ extern "C" int mb_hess_diag(mb_ctx* ctx, const mb_mat* L, const mb_mat* V, doubl
   MB_CHECK(V->rows * V->cols == L->rows, "mb_hess_diag: V has %lld entries for %lld cells",
            (long long)(V->rows * V->cols), (long long)L->rows);
   MB_CUDA(cudaSetDevice(ctx->device));
-  const int64_t n = L->rows;
   const int r = (int)L->cols;
-  const int64_t n_cta = std::max<int64_t>(1, min((int64_t)ctx->n_sm, ceil_div64(n, 8)));
-  const int64_t chunks = max(pick_chunks(ctx, n, r), n_cta);
   PassBuffers pb;
-  MB_TRY(carve(ctx, n, r, chunks, &pb));
-  MB_CUDA(cudaMemcpyAsync(pb.zdev, z_host, (size_t)r * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  if (n == 0) {
-    MB_CUDA(cudaMemsetAsync(pb.out, 0, (size_t)(r + 1) * sizeof(double), ctx->stream));
-  } else {
-    bool done = false;
-    if (ctx->opt_lossgrad == 0) MB_TRY(launch_stream<true>(ctx, L, pb.zdev, mu, V->p, &pb, n_cta, &done));
-    if (!done && ctx->opt_lossgrad != 1) MB_TRY(launch_fused<true>(ctx, L, pb.zdev, mu, V->p, &pb, n_cta, &done));
-    if (!done) {
-      MB_TRY(launch_rowdot<MODE_HESS>(ctx, L, pb.zdev, mu, V->p, pb.wv, nullptr, nullptr));
-      MB_TRY(colsum(ctx, L, pb.wv, true, &pb, pick_chunks(ctx, n, r), nullptr, 0));
-    }
-  }
-  MB_TRY(mb_allreduce_raw(ctx, pb.out, r));
+  MB_TRY(objective_pass<true>(ctx, L, V, mu, z_host, &pb));
   double* host;
   MB_TRY(mb_pinned(ctx, (size_t)r * sizeof(double), &host));
   MB_CUDA(cudaMemcpyAsync(host, pb.out, (size_t)r * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -691,22 +733,20 @@ extern "C" int mb_hess_diag(mb_ctx* ctx, const mb_mat* L, const mb_mat* V, doubl
   return 0;
 }
 
-// b = L^T t  [all-reduce]
+// b = L^T t  [tree reduce over the cells of all ranks]
 extern "C" int mb_gemv_t(mb_ctx* ctx, const mb_mat* L, const mb_mat* t, mb_mat* b) {
   MB_CHECK(ctx && L && t && b, "mb_gemv_t: null argument");
   MB_CHECK(t->rows * t->cols == L->rows && b->rows * b->cols == L->cols, "mb_gemv_t: shape mismatch");
   MB_CUDA(cudaSetDevice(ctx->device));
-  const int64_t n = L->rows;
   const int r = (int)L->cols;
   if (r == 0) return 0;
-  if (n == 0) {
-    MB_TRY(mb_mat_fill(ctx, b, 0.0));
-  } else {
-    int64_t chunks = pick_chunks(ctx, n, r);
-    PassBuffers pb;
-    MB_TRY(carve(ctx, 0, r, chunks, &pb));
-    MB_TRY(colsum(ctx, L, t->p, false, &pb, chunks, nullptr, 0));
-    MB_CUDA(cudaMemcpyAsync(b->p, pb.out, (size_t)r * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  }
-  return mb_allreduce_raw(ctx, b->p, r);
+  mb_chunks g;
+  MB_TRY(mb_chunk_grid(ctx, L, &g));
+  const SegGrid sg = make_seg_grid(g);
+  PassBuffers pb;
+  MB_TRY(carve(ctx, 0, r, sg.nseg, &pb));
+  MB_TRY(colsum(ctx, L, t->p, false, &pb, sg, nullptr));
+  MB_TRY(finish_reduce(ctx, g, sg, r, false, &pb));
+  MB_CUDA(cudaMemcpyAsync(b->p, pb.out, (size_t)r * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
 }

@@ -20,6 +20,11 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t);
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
   const char* (*GetErrorString)(ncclResult_t);
 };
 
@@ -44,6 +49,11 @@ int load_nccl() {
   SYM(CommDestroy, "ncclCommDestroy")
   SYM(AllReduce, "ncclAllReduce")
   SYM(AllGather, "ncclAllGather")
+  SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv")
+  SYM(Broadcast, "ncclBroadcast")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
   SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
   g_nccl.handle = h;
@@ -109,6 +119,25 @@ int mb_allreduce_raw(mb_ctx* ctx, double* p, int64_t count) {
   if (!ctx->comm || ctx->world == 1 || count == 0) return 0;
   MB_NCCL(g_nccl.AllReduce(p, p, (size_t)count, ncclFloat64, ncclSum, reinterpret_cast<ncclComm_t>(ctx->comm),
                            ctx->stream));
+  return 0;
+}
+
+int mb_sendrecv_raw(mb_ctx* ctx, const double* send, double* recv, int64_t count, int peer) {
+  MB_CHECK(ctx->comm && peer >= 0 && peer < ctx->world && peer != ctx->rank, "mb_sendrecv_raw: bad peer %d", peer);
+  if (count == 0) return 0;
+  ncclComm_t comm = reinterpret_cast<ncclComm_t>(ctx->comm);
+  MB_NCCL(g_nccl.GroupStart());
+  ncclResult_t a = g_nccl.Send(send, (size_t)count, ncclFloat64, peer, comm, ctx->stream);
+  ncclResult_t b = g_nccl.Recv(recv, (size_t)count, ncclFloat64, peer, comm, ctx->stream);
+  MB_NCCL(g_nccl.GroupEnd());
+  MB_NCCL(a);
+  MB_NCCL(b);
+  return 0;
+}
+
+int mb_bcast_raw(mb_ctx* ctx, double* p, int64_t count, int root) {
+  if (!ctx->comm || ctx->world == 1 || count == 0) return 0;
+  MB_NCCL(g_nccl.Broadcast(p, p, (size_t)count, ncclFloat64, root, reinterpret_cast<ncclComm_t>(ctx->comm), ctx->stream));
   return 0;
 }
 

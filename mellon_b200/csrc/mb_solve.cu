@@ -11,14 +11,12 @@ extern "C" int mb_gram(mb_ctx* ctx, const mb_mat* L, mb_mat* G) {
   MB_CUDA(cudaSetDevice(ctx->device));
   const int64_t r = L->cols;
   if (r == 0) return 0;
-  if (L->rows == 0) {
-    MB_TRY(mb_mat_fill(ctx, G, 0.0));
-  } else {
-    // G = L^T L: both operands k-major (k = cell index), lower tiles only, then mirror.
-    MB_TRY(mb_gemm_raw(ctx, true, true, r, r, L->rows, 1.0, L->p, r, L->p, r, 0.0, G->p, r, true));
-    MB_TRY(mb_mat_symmetrize(ctx, G));
-  }
-  return mb_allreduce_raw(ctx, G->p, r * r);
+  // G = L^T L: one k-major lower-tile product per chunk of the fixed reduction tree, chunk sums combined by the tree
+  // (across ranks when L is a row block of a sharded matrix), then mirrored
+  mb_chunks g;
+  MB_TRY(mb_chunk_grid(ctx, L, &g));
+  MB_TRY(mb_gemm_tn_cells(ctx, g, r, r, L->p, r, L->p, r, G->p, r, true));
+  return mb_mat_symmetrize(ctx, G);
 }
 
 extern "C" int mb_ridge_init(mb_ctx* ctx, const mb_mat* L, const mb_mat* t, double* z0_host) {

@@ -87,6 +87,7 @@ class FakeLib:
         self.err = b""
         self.launches = 0
         self.calls = []
+        self.shard = {}
 
     # ---- helpers ------------------------------------------------------------------------------
     def A(self, h):
@@ -106,6 +107,54 @@ class FakeLib:
             t = torch.from_numpy(a)
             dist.all_reduce(t)
         return a
+
+    # ---- the fixed reduction tree over the cell axis (mirrors csrc/mb_reduce.cu) -----------------
+    NCHUNK = 32
+
+    def mb_row_block(self, n, rank, world, lo, hi, cr):
+        c = max(1, -(-n // self.NCHUNK))
+        for ref, v in ((lo, min(n, (rank * self.NCHUNK // world) * c)),
+                       (hi, min(n, ((rank + 1) * self.NCHUNK // world) * c)), (cr, c)):
+            if ref is not None:
+                ref._obj.value = v
+        return 0
+
+    def mb_mat_set_shard(self, h, global_rows, row_lo):
+        a = self.A(h)
+        if global_rows < 0:
+            self.shard.pop(_val(h), None)
+            return 0
+        if row_lo < 0 or row_lo + a.shape[0] > global_rows:
+            return self._fail("mb_mat_set_shard: rows outside the matrix")
+        self.shard[_val(h)] = (int(global_rows), int(row_lo))
+        return 0
+
+    def _cell_sum(self, h, fn, shape):
+        """Tree sum over the cells of ``fn(i0, i1)`` (the contribution of local rows [i0, i1)): 32 global
+        chunks, each summed on its own, zero-padded all-reduce when the matrix is sharded, pairwise tree."""
+        a = self.A(h)
+        marked = _val(h) in self.shard
+        G, row_lo = self.shard.get(_val(h), (a.shape[0], 0))
+        sharded = marked and self.world > 1
+        cr = max(1, -(-G // self.NCHUNK))
+        if not sharded and (row_lo != 0 or a.shape[0] != G):
+            raise AssertionError("matrix marked as a row block but no communicator is attached")
+        leaves = np.zeros((self.NCHUNK,) + tuple(shape))
+        for c in range(self.NCHUNK):
+            i0, i1 = min(G, c * cr) - row_lo, min(G, (c + 1) * cr) - row_lo
+            if i1 > i0 and i0 >= 0 and i1 <= a.shape[0]:
+                leaves[c] = fn(i0, i1)
+        if sharded:
+            lo = min(G, (self.rank * self.NCHUNK // self.world) * cr)
+            hi = min(G, ((self.rank + 1) * self.NCHUNK // self.world) * cr)
+            if (lo, hi) != (row_lo, row_lo + a.shape[0]):
+                raise AssertionError(f"rank {self.rank} holds rows [{row_lo}, {row_lo + a.shape[0]}) but owns [{lo}, {hi})")
+            self._allreduce(leaves)
+        w = self.NCHUNK
+        while w > 1:
+            leaves = leaves[0:w:2] + leaves[1:w:2]
+            w //= 2
+        return leaves[0]
 
     def _fail(self, msg, code=-2):
         self.err = msg.encode()
@@ -190,6 +239,7 @@ class FakeLib:
 
     def mb_mat_free(self, ctx, h):
         self.m.pop(_val(h), None)
+        self.shard.pop(_val(h), None)
         return 0
 
     def mb_mat_upload(self, ctx, h, host, row0, nrows):
@@ -243,6 +293,19 @@ class FakeLib:
 
     def mb_mat_scale(self, ctx, h, s):
         self.A(h)[...] *= s
+        return 0
+
+    def mb_mat_combine(self, ctx, op, a, b, value):
+        x = self.A(a)
+        y = self.A(b) if b is not None and _val(b) else value
+        if op == nat.OP_ADD:
+            x[...] = x + y
+        elif op == nat.OP_MUL:
+            x[...] = x * y
+        elif op == nat.OP_POW:
+            x[...] = x ** value
+        else:
+            return self._fail("mb_mat_combine: bad op")
         return 0
 
     def mb_mat_row_sumsq(self, ctx, a, out):
@@ -333,26 +396,33 @@ class FakeLib:
         self.launches += 1
         self.calls.append("mb_gram")
         l = self.A(L)
-        g = l.T @ l
-        self.A(G)[...] = self._allreduce(g)
+        r = l.shape[1]
+        self.A(G)[...] = self._cell_sum(L, lambda i0, i1: l[i0:i1].T @ l[i0:i1], (r, r))
         return 0
 
     def mb_gemv_t(self, ctx, L, t, b):
-        v = self.A(L).T @ self.A(t).ravel()
-        self.A(b)[...] = self._allreduce(v).reshape(self.A(b).shape)
+        l, tv = self.A(L), self.A(t).ravel()
+        v = self._cell_sum(L, lambda i0, i1: l[i0:i1].T @ tv[i0:i1], (l.shape[1],))
+        self.A(b)[...] = v.reshape(self.A(b).shape)
         return 0
 
     def mb_ridge_init(self, ctx, L, t, z0):
         self.calls.append("mb_ridge_init")
-        l = self.A(L)
-        g = self._allreduce(l.T @ l) + np.eye(l.shape[1])
-        b = self._allreduce(l.T @ self.A(t).ravel())
-        _host(z0, l.shape[1])[:] = np.linalg.solve(g, b)
+        l, tv = self.A(L), self.A(t).ravel()
+        r = l.shape[1]
+        g = self._cell_sum(L, lambda i0, i1: l[i0:i1].T @ l[i0:i1], (r, r)) + np.eye(r)
+        b = self._cell_sum(L, lambda i0, i1: l[i0:i1].T @ tv[i0:i1], (r,))
+        _host(z0, r)[:] = np.linalg.solve(g, b)
         return 0
 
     def mb_gemm(self, ctx, ta, tb, alpha, A, B, beta, Cm):
         self.launches += 1
         a, b, c = self.A(A), self.A(B), self.A(Cm)
+        if ta and not tb and _val(A) in self.shard:
+            if alpha != 1.0 or beta != 0.0:
+                return self._fail("mb_gemm: a product contracted over sharded cells takes alpha = 1, beta = 0")
+            c[...] = self._cell_sum(A, lambda i0, i1: a[i0:i1].T @ b[i0:i1], c.shape)
+            return 0
         prod = alpha * ((a.T if ta else a) @ (b.T if tb else b))
         c[...] = prod + (beta * c if beta != 0.0 else 0.0)
         return 0
@@ -361,13 +431,16 @@ class FakeLib:
     def mb_loss_grad(self, ctx, L, V, sum_vdr, mu, k, z, loss, grad):
         self.launches += 1
         self.calls.append("mb_loss_grad")
-        l = self.A(L)
+        l, v = self.A(L), self.A(V).ravel()
         r = l.shape[1]
         zv = _host(z, r).copy()
-        f = l @ zv + mu
-        Aexp = np.exp(f + self.A(V).ravel())
-        part = np.concatenate([l.T @ (Aexp - 1.0), [np.sum(f - Aexp)]])
-        part = self._allreduce(part)
+
+        def chunk(i0, i1):  # everything from the chunk's own rows: the same arithmetic whoever holds them
+            f = l[i0:i1] @ zv + mu
+            Aexp = np.exp(f + v[i0:i1])
+            return np.concatenate([l[i0:i1].T @ (Aexp - 1.0), [np.sum(f - Aexp)]])
+
+        part = self._cell_sum(L, chunk, (r + 1,))
         _host(grad, r)[:] = zv + part[:r]
         loss._obj.value = 0.5 * float(zv @ zv) + 0.5 * k * np.log(2 * np.pi) - (part[r] + sum_vdr)
         return 0
@@ -378,11 +451,15 @@ class FakeLib:
         return 0
 
     def mb_hess_diag(self, ctx, L, V, mu, z, diag):
-        l = self.A(L)
+        l, v = self.A(L), self.A(V).ravel()
         r = l.shape[1]
-        Aexp = np.exp(l @ _host(z, r) + mu + self.A(V).ravel())
-        d = self._allreduce(np.einsum("i,ij,ij->j", Aexp, l, l))
-        _host(diag, r)[:] = 1.0 + d
+        zv = _host(z, r).copy()
+
+        def chunk(i0, i1):
+            Aexp = np.exp(l[i0:i1] @ zv + mu + v[i0:i1])
+            return np.einsum("i,ij,ij->j", Aexp, l[i0:i1], l[i0:i1])
+
+        _host(diag, r)[:] = 1.0 + self._cell_sum(L, chunk, (r,))
         return 0
 
     def mb_syevd(self, ctx, a, w):

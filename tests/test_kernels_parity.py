@@ -399,3 +399,60 @@ def test_nn_distances_known_answers(be):
     np.testing.assert_allclose(be.nn_distances(x), np.sqrt(2.0) * np.ones(3), rtol=1e-15)
     x = np.array([[1.0, 1.0], [1.0, 1.0], [1.0, 1.0]])
     np.testing.assert_array_equal(be.nn_distances(x), np.zeros(3))
+
+
+# ---- expressions that do not fit ONE device program: split at the root, combined on the device -----------------
+class _UserKernel(mb.cov.Covariance):
+    """A user-defined kernel (subclasses overriding k must keep working)."""
+
+    def k(self, x, y):
+        return np.exp(-np.abs(np.asarray(x)[:, None, 0] - np.asarray(y)[None, :, 0]))
+
+
+class _ExtendedMatern(mb.cov.Matern52):
+    def k(self, x, y):
+        return 2.0 * super().k(x, y)
+
+
+def test_large_and_user_defined_expressions_are_split_not_evaluated_on_the_host(be):
+    rng = np.random.default_rng(5)
+    x, y = rng.random((70, 4)), rng.random((33, 4))
+    leaves = [mb.cov.Matern52(1.0), mb.cov.Matern32(2.0), mb.cov.ExpQuad(0.5), mb.cov.Matern52(3.0, active_dims=[0, 2]),
+              mb.cov.ExpQuad(1.5), mb.cov.Exponential(0.7)]
+    six = leaves[0] + leaves[1] + leaves[2] * leaves[3] + leaves[4] * 0.3 + leaves[5] ** 2.0       # 6 leaves > MB_MAX_LEAVES
+    oleaves = [O.Matern52(1.0), O.Matern32(2.0), O.ExpQuad(0.5), O.Matern52(3.0, active_dims=[0, 2]), O.ExpQuad(1.5),
+               O.Exponential(0.7)]
+    ref = (oleaves[0](x, y) + oleaves[1](x, y) + oleaves[2](x, y) * oleaves[3](x, y) + oleaves[4](x, y) * 0.3
+           + oleaves[5](x, y) ** 2.0)
+    assert not be.supports(six, 4)
+    before = list(getattr(be.lib, "calls", []))
+    np.testing.assert_allclose(six(x, y), ref, rtol=0, atol=5e-13)
+    if hasattr(be.lib, "calls"):   # the test double records the entry points: every leaf went through mb_cov_build
+        assert be.lib.calls[len(before):].count("mb_cov_build") >= 2
+    refd = sum(float(np.squeeze(k(x[:1], x[:1]))) for k in oleaves[:2]) + float(np.squeeze(oleaves[2](x[:1], x[:1]) * oleaves[3](x[:1], x[:1]))) \
+        + 0.3 * float(np.squeeze(oleaves[4](x[:1], x[:1]))) + float(np.squeeze(oleaves[5](x[:1], x[:1]))) ** 2
+    np.testing.assert_allclose(six.diag(x)[0], refd, rtol=1e-12)
+    # a user kernel inside Mul / Add / Pow, and a user class extending a stock kernel through super().k
+    user = _UserKernel()
+    np.testing.assert_allclose((user * mb.cov.Matern52(1.0))(x, y), user.k(x, y) * O.Matern52(1.0)(x, y), atol=5e-13)
+    np.testing.assert_allclose((user + 1.0)(x, y), user.k(x, y) + 1.0, atol=5e-13)
+    np.testing.assert_allclose(((user + mb.cov.Matern32(1.0)) ** 2.0)(x, y), (user.k(x, y) + O.Matern32(1.0)(x, y)) ** 2,
+                               atol=5e-13)
+    np.testing.assert_allclose(_ExtendedMatern(1.0)(x, y), 2.0 * O.Matern52(1.0)(x, y), atol=5e-13)
+    np.testing.assert_allclose((user * mb.cov.Matern52(1.0)).diag(x), np.ones(70) * O.Matern52(1.0)(x[:1], x[:1])[0, 0],
+                               rtol=1e-12)
+
+
+def test_estimator_fits_with_an_expression_too_large_for_one_program(be):
+    rng = np.random.default_rng(6)
+    X = rng.random((400, 3))
+    nn = O.compute_nn_distances(X)
+    lm = X[:25].copy()
+    cov = mb.cov.Matern52(0.9) + mb.cov.Matern32(1.1) + mb.cov.ExpQuad(0.8) + mb.cov.Matern52(2.0) + mb.cov.ExpQuad(1.7) * 0.5
+    ocov = O.Add(O.Add(O.Add(O.Add(O.Matern52(0.9), O.Matern32(1.1)), O.ExpQuad(0.8)), O.Matern52(2.0)),
+                 O.Mul(O.ExpQuad(1.7), 0.5))
+    est = mb.DensityEstimator(cov_func=cov, landmarks=lm, nn_distances=nn)
+    dens = est.fit_predict(X)
+    ref = O.fit_density(X, cov_func=ocov, landmarks=lm, nn_distances=nn)
+    np.testing.assert_allclose(dens, ref.log_density_x, rtol=1e-5)
+    np.testing.assert_allclose(est.predict(X[:50]), O.predict_density(ref, X, X[:50]), rtol=1e-5)

@@ -3,9 +3,11 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
         tools/check_multi_gpu.py
 
-Every rank fits the same (ragged) cell matrix sharded over the ranks through the real CUDA library with
-NCCL all-reduces; rank 0 compares with the CPU oracle (log density 1e-5 relative, north_star) and with the
-Nystroem and Laplace variants; all ranks must hold identical bits."""
+Every rank fits the same (ragged) cell matrix sharded over the ranks through the real CUDA library (sums over
+cells through the fixed 32-leaf tree, NCCL between ranks); rank 0 compares with the CPU oracle (log density 1e-5
+relative, north_star) and with the Nystroem and Laplace variants; all ranks must hold identical bits, AND those
+bits must equal what ONE GPU computes alone (rank 0 repeats everything unsharded): results do not depend on the
+number of GPUs.  FULL / FULL_NYSTROEM fits (replicated factors) run too: they must not be summed over the ranks."""
 import hashlib
 import os
 import sys
@@ -41,8 +43,31 @@ def main():
     yv = np.stack([np.sin(3 * X[:, 0]) + X[:, 1], np.cos(2 * X[:, 2])], axis=1)
     fe = mb.FunctionEstimator(landmarks=lm, ls=0.8, sigma=np.array([0.2, 0.5]), obs_variance=True).fit(X, yv)
     fe_pred, fe_lev, fe_var = fe.predict(Y), fe.leverage(), fe.get_obs_variance(Y)
-    digest = hashlib.sha256(dens.tobytes() + pred.tobytes() + dens_nys.tobytes() + fe_pred.tobytes() + fe_lev.tobytes()
-                            + fe_var.tobytes()).hexdigest()
+    Xs = np.ascontiguousarray(X[:700])
+    nns = be.nn_distances(Xs)
+    full = mb.DensityEstimator(n_landmarks=0, nn_distances=nns, predictor_with_uncertainty=True)
+    dens_full = full.fit_predict(Xs)
+    dens_fnys = mb.DensityEstimator(n_landmarks=0, rank=0.9, nn_distances=nns).fit_predict(Xs)
+
+    def sha(*arrays):
+        return hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in arrays)).hexdigest()
+
+    parts = {"log_density": dens, "predict": pred, "nystroem": dens_nys, "laplace_std": est.pre_transformation_std,
+             "function_predict": fe_pred, "function_leverage": fe_lev, "function_obs_variance": fe_var,
+             "full": dens_full, "full_nystroem": dens_fnys}
+    digest = sha(*parts.values())
+    one_gpu = None
+    if world > 1 and rank == 0:
+        # the same work on ONE GPU (nothing sharded), inside this job: bits must match the sharded results
+        with be.replicated():
+            e1 = mb.DensityEstimator(landmarks=lm, nn_distances=nn, check_rank=False, predictor_with_uncertainty=True)
+            d1 = e1.fit_predict(X)
+            n1 = mb.DensityEstimator(landmarks=lm, nn_distances=nn, rank=200, check_rank=False).fit_predict(X)
+            f1 = mb.FunctionEstimator(landmarks=lm, ls=0.8, sigma=np.array([0.2, 0.5]), obs_variance=True).fit(X, yv)
+            alone = {"log_density": d1, "predict": e1.predict(Y), "nystroem": n1, "laplace_std": e1.pre_transformation_std,
+                     "function_predict": f1.predict(Y), "function_leverage": f1.leverage(),
+                     "function_obs_variance": f1.get_obs_variance(Y)}
+        one_gpu = {k: (sha(v) == sha(parts[k]), float(np.max(np.abs(np.asarray(v) - np.asarray(parts[k]))))) for k, v in alone.items()}
     import torch
     import torch.distributed as td
 
@@ -69,8 +94,14 @@ def main():
             "laplace_std": rel(est.pre_transformation_std,
                                O.laplace_std_from_diag(O.hessian_diag(ref.L, nn_ref, ref.d, ref.mu, est.pre_transformation))),
         }
+        ref_full = O.fit_density(Xs, nn_distances=O.compute_nn_distances(Xs), n_landmarks=0)
+        ref_fnys = O.fit_density(Xs, nn_distances=O.compute_nn_distances(Xs), n_landmarks=0, rank=0.9)
+        errs["full_log_density"] = rel(dens_full, ref_full.log_density_x)
+        errs["full_nystroem_log_density"] = rel(dens_fnys, ref_fnys.log_density_x)
         print(f"world={world} identical_bits_on_all_ranks={same} nfev={est.opt_state.num_fun_eval} errors={errs}")
-        ok = same and errs["nn_distances"] < 1e-12 and errs["log_density"] < 1e-5 and errs["predict"] < 1e-5 \
+        print(f"world={world} same_bits_as_one_gpu (identical, max |diff|): {one_gpu}")
+        inv = one_gpu is None or all(v[0] for v in one_gpu.values())
+        ok = same and inv and errs["full_log_density"] < 1e-5 and errs["full_nystroem_log_density"] < 1e-5 and errs["nn_distances"] < 1e-12 and errs["log_density"] < 1e-5 and errs["predict"] < 1e-5 \
             and errs["nystroem_log_density"] < 1e-5 and errs["function_predict"] < 1e-6 and errs["function_leverage"] < 1e-6 \
             and errs["function_obs_variance"] < 1e-6
         print("MULTI_GPU_PARITY", "OK" if ok else "FAILED")
