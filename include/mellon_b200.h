@@ -100,7 +100,8 @@ int mb_timer_stop(mb_ctx* ctx, int slot, double* ms);
  * time since the last reset, plus the ALGORITHMIC work of those launches (`work`: bytes for the
  * HBM-bound classes, flops for the GEMM class).  Classes: 0 = K1 covariance build (x != y),
  * 1 = K7 covariance mat-vec, 2 = FP64 GEMM tiles (K3/K4/K2 updates), 3 = K5/K6 fused objective
- * pass, 4 = everything else that is timed (the symmetric landmark covariance K_MM). */
+ * pass, 4 = everything else that is timed (the symmetric landmark covariance K_MM), 5 = int8 digit-slice GEMMs
+ * on tcgen05 (work: float64-equivalent flops). */
 int mb_prof_enable(mb_ctx* ctx, int on);
 int mb_prof_reset(mb_ctx* ctx);
 int mb_prof_read(mb_ctx* ctx, int cls, int64_t* count, double* ms, double* work);
@@ -111,7 +112,9 @@ int mb_flush_l2(mb_ctx* ctx);
  *   "gemm"     1 = DFMA reference GEMM, 2 = 8-warp DMMA tiles, 3 = no split-k, 4 = generic operand loaders
  *   "trsm"     1 = 32-wide substitution leaves for TRSM / Cholesky (no inverted 128-blocks, no blocked TRSV)
  *   "lossgrad" 1 = two-pass objective, 2 = register-fused single pass (0 = bulk-TMA ring)
- *   "graph"    0 = launch the Cholesky on the stream instead of replaying its CUDA graph */
+ *   "graph"    0 = launch the Cholesky on the stream instead of replaying its CUDA graph
+ *   "i8"       0 = Gram products of large factors on the FP64 DMMA tiles instead of tcgen05 kind::i8 digit slices
+ *              (the default, 1: chunk >= 2048 cells and r >= 512) */
 int mb_set_option(mb_ctx* ctx, const char* key, int value);
 
 /* pinned (page-locked) host buffers, so uploads / the streaming predictor overlap with compute */

@@ -83,6 +83,9 @@ extern "C" int mb_ctx_destroy(mb_ctx* c) {
   if (c->scratch) cudaFree(c->scratch);
   if (c->flush_buf) cudaFree(c->flush_buf);
   if (c->gemm_ws) cudaFree(c->gemm_ws);
+  if (c->i8_ws) cudaFree(c->i8_ws);
+  if (c->i8_tiles) cudaFree(c->i8_tiles);
+  if (c->i8_status) cudaFree(c->i8_status);
   if (c->trsm_ws) cudaFree(c->trsm_ws);
   mb_invalidate_graphs(c);
   if (c->potrf_buf) cudaFree(c->potrf_buf);
@@ -201,6 +204,7 @@ extern "C" int mb_set_option(mb_ctx* c, const char* key, int value) {
   else if (!strcmp(key, "trsm")) c->opt_trsm = value;
   else if (!strcmp(key, "graph")) c->opt_graph = value;
   else if (!strcmp(key, "lossgrad")) c->opt_lossgrad = value;
+  else if (!strcmp(key, "i8")) c->opt_i8 = value;
   else MB_CHECK(false, "mb_set_option: unknown key %s", key);
   return 0;
 }

@@ -51,11 +51,20 @@ int mb_tree_reduce_small(mb_ctx* ctx, const mb_chunks& g, double* leaves, int64_
 // tree over matrices too large to gather: `acc` holds this rank's tree sum of its own leaves on entry and the global
 // tree sum on return (butterfly exchange for power-of-two worlds whose ranks own aligned subtrees)
 int mb_tree_combine_ranks(mb_ctx* ctx, const mb_chunks& g, double* acc, int64_t count);
-int mb_axpy_raw(mb_ctx* ctx, double* dst, const double* src, int64_t count);  // dst = dst + src (elementwise)
+int mb_axpy_raw(mb_ctx* ctx, double* dst, const double* src, int64_t count);
+// int8 digit-slice Gram of one block of cells (mb_i8.cu): out (r x r dense, tiles on / below the diagonal) = A^T A
+bool mb_i8_gram_usable(mb_ctx* ctx, int64_t rows, int64_t r);
+int mb_i8_gram_leaf(mb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t r, double* out);
+int mb_i8_check(mb_ctx* ctx);
+// C = beta C + alpha A B^T on int8 digit slices (A: n x k, B: p x k row-major; beta 0 or 1); rows_total: the GLOBAL
+// number of rows of the row-sharded operand (the path is chosen from it, not from the local row count)
+bool mb_i8_nt_usable(mb_ctx* ctx, int64_t rows_total, int64_t p, int64_t k);
+int mb_i8_gemm_nt(mb_ctx* ctx, int64_t n, int64_t p, int64_t k, double alpha, const double* A, int64_t lda,
+                  const double* B, int64_t ldb, int beta, double* C, int64_t ldc);  // dst = dst + src (elementwise)
 
 // kernel classes for the in-library stopwatch (mb_prof_*): CUDA events around each launch
 enum { MB_PROF_COV = 0, MB_PROF_MATVEC = 1, MB_PROF_GEMM = 2, MB_PROF_LOSSGRAD = 3, MB_PROF_OTHER = 4,
-       MB_PROF_NCLS = 5 };
+       MB_PROF_I8 = 5, MB_PROF_NCLS = 6 };
 
 struct mb_prof_span {
   int cls;
@@ -91,6 +100,14 @@ struct mb_ctx {
   size_t trsm_ws_bytes = 0;
   double* gemm_ws = nullptr;           // split-k partial tiles (own buffer: GEMMs run inside scratch users)
   size_t gemm_ws_bytes = 0;
+  // int8 digit-slice GEMMs (mb_i8.cu): digit operands / scales / partials, tile list, error flag
+  void* i8_ws = nullptr;
+  size_t i8_ws_bytes = 0;
+  int2* i8_tiles = nullptr;
+  int64_t i8_tiles_r = -1;
+  int i8_ntiles = 0;
+  int* i8_status = nullptr;
+  int opt_i8 = 1;        // 1 = Gram products of large factors on tcgen05 kind::i8 digit slices, 0 = FP64 DMMA tiles
   // NCCL
   void* comm = nullptr;
   int rank = 0, world = 1;

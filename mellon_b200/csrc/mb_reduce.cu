@@ -161,6 +161,9 @@ int mb_gemm_tn_cells(mb_ctx* ctx, const mb_chunks& g, int64_t m, int64_t n, cons
   const int64_t count = m * n;
   const int world = g.sharded ? ctx->world : 1, me = g.sharded ? ctx->rank : 0;
   auto leaf_empty = [&](int c) { return (int64_t)c * g.cr >= g.G; };
+  // symmetric products of large factors run on the tcgen05 int8 digit slices; the choice depends on the GLOBAL chunk
+  // size and the width only, so it is the same for every number of ranks
+  const bool i8 = lower_only && A == B && lda == ldb && m == n && mb_i8_gram_usable(ctx, std::min(g.cr, g.G), m);
 
   std::vector<Node> mine;
   canonical_nodes(g.c_lo, g.c_hi, &mine);
@@ -181,8 +184,12 @@ int mb_gemm_tn_cells(mb_ctx* ctx, const mb_chunks& g, int64_t m, int64_t n, cons
       if (!leaf_empty(c) && i1 > i0) {
         leaf.buf = pool.get();
         MB_CHECK(leaf.buf, "mb_gemm_tn_cells: buffer pool exhausted");
-        MB_TRY(mb_gemm_raw(ctx, true, true, m, n, i1 - i0, 1.0, A + i0 * lda, lda, B + i0 * ldb, ldb, 0.0, leaf.buf, n,
-                           lower_only));
+        if (i8) {
+          MB_TRY(mb_i8_gram_leaf(ctx, A + i0 * lda, lda, i1 - i0, m, leaf.buf));
+        } else {
+          MB_TRY(mb_gemm_raw(ctx, true, true, m, n, i1 - i0, 1.0, A + i0 * lda, lda, B + i0 * ldb, ldb, 0.0, leaf.buf, n,
+                             lower_only));
+        }
       }
       MB_TRY(push_merge(ctx, &st, leaf, count, &pool));
     }
@@ -217,6 +224,7 @@ int mb_gemm_tn_cells(mb_ctx* ctx, const mb_chunks& g, int64_t m, int64_t n, cons
     }
   }
   MB_CHECK(st.size() == 1 && st[0].start == 0 && st[0].size == MB_NCHUNK, "mb_gemm_tn_cells: tree did not close");
+  if (i8) MB_TRY(mb_i8_check(ctx));
   if (st[0].buf) {
     MB_CUDA(cudaMemcpyAsync(C, st[0].buf, (size_t)count * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   } else {

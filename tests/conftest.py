@@ -23,11 +23,16 @@ def pytest_configure(config):
 
 
 def _have_gpu():
+    """True when the CUDA library sees a device.  A box that HAS a GPU but cannot load the library (stale build,
+    missing symbol) must not turn the GPU suite into 385 silent skips: that is an error, raised here."""
+    gpu_node = os.path.exists("/dev/nvidia0")
     try:
         from mellon_b200 import _native as nat
 
         return nat.device_count() > 0
-    except Exception:
+    except Exception as e:
+        if gpu_node:
+            raise pytest.UsageError(f"a GPU is present but libmellon_b200.so cannot be used: {e}")
         return False
 
 

@@ -456,3 +456,40 @@ def test_estimator_fits_with_an_expression_too_large_for_one_program(be):
     ref = O.fit_density(X, cov_func=ocov, landmarks=lm, nn_distances=nn)
     np.testing.assert_allclose(dens, ref.log_density_x, rtol=1e-5)
     np.testing.assert_allclose(est.predict(X[:50]), O.predict_density(ref, X, X[:50]), rtol=1e-5)
+
+
+# ---- K4 on tcgen05 kind::i8 digit slices (csrc/mb_i8.cu): chunks of >= 2048 cells, r >= 512 ---------------------
+@pytest.mark.parametrize("n,r", [(65536, 512), (70001, 640), (66003, 777), (131072, 1030)])
+def test_gram_on_int8_digit_slices(be, n, r):
+    """The Gram matrix of a tall factor through the int8 digit-slice path: every entry within float64 rounding of the
+    exact product, measured against (|L|^T |L|)_ij like a float64 dot product would be; columns of very different
+    magnitude (a whitened covariance block) and ragged shapes; identical to rounding with the FP64 DMMA path."""
+    if be.name != "cuda":
+        pytest.skip("the int8 digit-slice path exists in the CUDA library only (the test double's Gram is NumPy's)")
+    rng = np.random.default_rng(n + r)
+    colscale = 10.0 ** (-6.0 * np.arange(r) / r)
+    L = (rng.random((n, 1)) - 0.5 + 0.3 * (rng.random((n, r)) - 0.5)) * colscale
+    Ld = be.upload(L, sharded=True)
+    G = be.gram(Ld).numpy()
+    be.set_option("i8", 0)
+    try:
+        G64 = be.gram(Ld).numpy()
+    finally:
+        be.set_option("i8", 1)
+    ref = L.T @ L
+    bound = np.abs(L).T @ np.abs(L)
+    assert np.array_equal(G, G.T)
+    # float64 accumulation over n terms (the reference itself) is good to ~ sqrt(n) eps of the bound
+    assert np.max(np.abs(G - ref) / bound) < 2e-14
+    assert np.max(np.abs(G - G64) / bound) < 2e-14
+    t = rng.standard_normal(n)
+    z0 = be.ridge_init(Ld, t)
+    assert rel_err(z0, O.ridge_normal_equations(L, t)) < 1e-8
+
+
+def test_gram_int8_rejects_non_finite_operands(be):
+    L = np.random.default_rng(0).random((65536, 512))
+    L[70, 3] = np.inf
+    if be.name == "cuda":
+        with pytest.raises(Exception, match="non-finite"):
+            be.gram(be.upload(L, sharded=True))
