@@ -137,9 +137,11 @@ tri_inv_blocks_kernel(const double* __restrict__ L, int64_t ldl, int64_t m, doub
   tri_inv_block(Tsh, xw, rdiag, w, inv + (int64_t)blockIdx.x * IB * IB);
 }
 
-// X[:, c0:c0+w] <- X[:, c0:c0+w] Lp[c0:c0+w, c0:c0+w]^-T with GEMM leaves on the inverted diagonal blocks
+// X[:, c0:c0+w] <- X[:, c0:c0+w] Lp[c0:c0+w, c0:c0+w]^-T with GEMM leaves on the inverted diagonal blocks.
+// `i8`: the large off-diagonal updates X2 -= X1 L21^T run on the tcgen05 int8 digit slices (mb_i8.cu); the choice
+// depends on the GLOBAL row count and the block widths only.
 int trsm_inv_rec(mb_ctx* ctx, const double* Lp, int64_t ldl, const double* inv, int64_t c0, int64_t w, double* X,
-                 int64_t ldx, int64_t nrows) {
+                 int64_t ldx, int64_t nrows, int64_t rows_total) {
   if (w <= 0) return 0;
   if (w <= IB) {
     // in place: a CTA consumes its whole 128 x w input tile before it stores the same tile
@@ -147,10 +149,14 @@ int trsm_inv_rec(mb_ctx* ctx, const double* Lp, int64_t ldl, const double* inv, 
     return mb_gemm_rows_raw(ctx, false, false, nrows, w, w, 1.0, X + c0, ldx, Tinv, IB, 0.0, X + c0, ldx);
   }
   const int64_t w1 = ((w / 2 + IB - 1) / IB) * IB;
-  MB_TRY(trsm_inv_rec(ctx, Lp, ldl, inv, c0, w1, X, ldx, nrows));
-  MB_TRY(mb_gemm_rows_raw(ctx, false, false, nrows, w - w1, w1, -1.0, X + c0, ldx, Lp + (c0 + w1) * ldl + c0, ldl, 1.0,
-                          X + c0 + w1, ldx));
-  return trsm_inv_rec(ctx, Lp, ldl, inv, c0 + w1, w - w1, X, ldx, nrows);
+  MB_TRY(trsm_inv_rec(ctx, Lp, ldl, inv, c0, w1, X, ldx, nrows, rows_total));
+  if (mb_i8_nt_usable(ctx, rows_total, w - w1, w1)) {
+    MB_TRY(mb_i8_gemm_nt(ctx, nrows, w - w1, w1, -1.0, X + c0, ldx, Lp + (c0 + w1) * ldl + c0, ldl, 1, X + c0 + w1, ldx));
+  } else {
+    MB_TRY(mb_gemm_rows_raw(ctx, false, false, nrows, w - w1, w1, -1.0, X + c0, ldx, Lp + (c0 + w1) * ldl + c0, ldl, 1.0,
+                            X + c0 + w1, ldx));
+  }
+  return trsm_inv_rec(ctx, Lp, ldl, inv, c0 + w1, w - w1, X, ldx, nrows, rows_total);
 }
 
 int potrf_rec(mb_ctx* ctx, double* A, int64_t lda, int64_t off, int64_t n, int* info) {
@@ -484,7 +490,7 @@ int potrf128_rec(mb_ctx* ctx, double* A, int64_t lda, int64_t off, int64_t n, in
   const int64_t n1 = ((n / 2 + IB - 1) / IB) * IB, n2 = n - n1;
   MB_TRY(potrf128_rec(ctx, A, lda, off, n1, info, inv));
   double* A21 = A + (off + n1) * lda + off;
-  MB_TRY(trsm_inv_rec(ctx, D, lda, inv + (off / IB) * IB * IB, 0, n1, A21, lda, n2));
+  MB_TRY(trsm_inv_rec(ctx, D, lda, inv + (off / IB) * IB * IB, 0, n1, A21, lda, n2, 0));
   double* A22 = A + (off + n1) * lda + off + n1;
   MB_TRY(mb_gemm_raw(ctx, false, false, n2, n2, n1, -1.0, A21, lda, A21, lda, 1.0, A22, lda, true));
   return potrf128_rec(ctx, A, lda, off + n1, n2, info, inv);
@@ -579,7 +585,8 @@ int mb_trsm_right_lt_raw(mb_ctx* ctx, const double* Lp, int64_t ldl, int64_t m, 
   const int64_t nb = ceil_div64(m, IB);
   MB_TRY(mb_trsm_ws(ctx, m));
   MB_LAUNCH(ctx, tri_inv_blocks_kernel, (int)nb, IBT, IB_SMEM, Lp, ldl, m, ctx->trsm_ws);
-  return trsm_inv_rec(ctx, Lp, ldl, ctx->trsm_ws, 0, m, X, ldx, nrows);
+  MB_TRY(trsm_inv_rec(ctx, Lp, ldl, ctx->trsm_ws, 0, m, X, ldx, nrows, std::max(nrows, rows_total)));
+  return (ctx->opt_i8 && ctx->i8_status) ? mb_i8_check(ctx) : 0;
 }
 
 // direct (stream) Cholesky of the n x n matrix at A; the strict upper triangle is zeroed

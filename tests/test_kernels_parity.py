@@ -493,3 +493,30 @@ def test_gram_int8_rejects_non_finite_operands(be):
     if be.name == "cuda":
         with pytest.raises(Exception, match="non-finite"):
             be.gram(be.upload(L, sharded=True))
+
+
+@pytest.mark.parametrize("n,m", [(8192, 1024), (20011, 1500), (9000, 2600)])
+def test_trsm_right_with_int8_updates(be, n, m):
+    """K3 at sizes where the large off-diagonal updates X2 -= X1 L21^T run on the tcgen05 int8 digit slices
+    (>= 8192 rows, k >= 512, >= 256 output columns): same tolerance as the FP64 path, and the two agree to rounding.
+    Rows of very different magnitude (every row carries its own scale) and a ragged row count."""
+    if be.name != "cuda":
+        pytest.skip("the int8 digit-slice path exists in the CUDA library only")
+    rng = np.random.default_rng(n + m)
+    Lp = np.linalg.cholesky(_spd(m, m, 1e4))
+    X = rng.standard_normal((n, m)) * 10.0 ** rng.uniform(-4, 2, size=(n, 1))
+    Lpd = be.upload(Lp)
+    out = be.trsm_right_lt(Lpd, be.upload(X.copy())).numpy()
+    be.set_option("i8", 0)
+    try:
+        out64 = be.trsm_right_lt(Lpd, be.upload(X.copy())).numpy()
+    finally:
+        be.set_option("i8", 1)
+    ref = solve_triangular(Lp, X.T, lower=True).T
+    rownorm = np.max(np.abs(ref), axis=1, keepdims=True)
+    assert np.max(np.abs(out - ref) / rownorm) < 1e-11
+    assert np.max(np.abs(out - out64) / rownorm) < 1e-11
+    # the sharded view of the same rows gives the same bits (the path is chosen from the global row count)
+    half = be.trsm_right_lt(Lpd, be.upload(X[: n // 2].copy())).numpy()
+    if n // 2 >= 8192:
+        assert np.array_equal(half, out[: n // 2])
