@@ -105,6 +105,11 @@ int mb_timer_stop(mb_ctx* ctx, int slot, double* ms);
 int mb_prof_enable(mb_ctx* ctx, int on);
 int mb_prof_reset(mb_ctx* ctx);
 int mb_prof_read(mb_ctx* ctx, int cls, int64_t* count, double* ms, double* work);
+/* NVTX ranges (nvtx3, no cost unless a profiler is attached): every entry point of this library opens a range named
+ * "mellon_b200: <stage>"; these two let the host side bracket its own stages (the L-BFGS-B loop of
+ * inference.py:272-288, prepare_inference) so that one timeline shows Lp / L / Gram / L-BFGS-B / transform. */
+int mb_range_push(const char* name);
+int mb_range_pop(void);
 /* overwrite a scratch buffer larger than L2 (cache flush between timed iterations) */
 int mb_flush_l2(mb_ctx* ctx);
 /* select kernel variants for A/B measurements and parity tests (0 is always the default path):

@@ -73,6 +73,8 @@ SIGNATURES = {
     "mb_prof_enable": (_i, [_vp, _i]),
     "mb_prof_reset": (_i, [_vp]),
     "mb_prof_read": (_i, [_vp, _i, C.POINTER(_i64), _pd, _pd]),
+    "mb_range_push": (_i, [C.c_char_p]),
+    "mb_range_pop": (_i, []),
     "mb_flush_l2": (_i, [_vp]),
     "mb_set_option": (_i, [_vp, C.c_char_p, _i]),
     "mb_host_alloc": (_i, [_i64, C.POINTER(_vp)]),

@@ -232,6 +232,15 @@ class CudaBackend:
             out[name] = (n.value, ms.value, work.value)
         return out
 
+    @contextlib.contextmanager
+    def range(self, name):
+        """NVTX range around a host-side stage (shows up next to the library's own per-entry-point ranges)."""
+        self.lib.mb_range_push(("mellon_b200: " + name).encode())
+        try:
+            yield
+        finally:
+            self.lib.mb_range_pop()
+
     def flush_l2(self):
         nat.check(self.lib.mb_flush_l2(self.ctx))
 

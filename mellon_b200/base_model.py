@@ -253,7 +253,10 @@ class BaseEstimator:
         (``base_model.py:433-446``)."""
         if getattr(self, attribute) is not None:
             return
-        setattr(self, attribute, getattr(self, "_compute_" + attribute)())
+        from .backend import get_backend
+
+        with get_backend().range("prepare " + attribute):   # NVTX: one range per stage of prepare_inference
+            setattr(self, attribute, getattr(self, "_compute_" + attribute)())
 
     def prepare_inference(self, x):  # pragma: no cover - interface
         ...

@@ -197,6 +197,16 @@ extern "C" int mb_prof_read(mb_ctx* c, int cls, int64_t* count, double* ms, doub
   return 0;
 }
 
+// host-side NVTX ranges for the callers above the ABI (the L-BFGS-B loop, the estimator stages)
+extern "C" int mb_range_push(const char* name) {
+  nvtxRangePushA(name ? name : "mellon_b200");
+  return 0;
+}
+extern "C" int mb_range_pop(void) {
+  nvtxRangePop();
+  return 0;
+}
+
 extern "C" int mb_set_option(mb_ctx* c, const char* key, int value) {
   MB_CHECK(c && key, "mb_set_option: null");
   if (!strcmp(key, "gemm")) c->opt_gemm = value;

@@ -672,6 +672,7 @@ int mb_potrf_raw(mb_ctx* ctx, double* A, int64_t n, int64_t lda, int* info_dev) 
 }
 
 extern "C" int mb_potrf(mb_ctx* ctx, mb_mat* a) {
+  MB_RANGE("mellon_b200: K2 potrf");
   MB_CHECK(ctx && a, "mb_potrf: null argument");
   MB_CHECK(a->rows == a->cols, "mb_potrf: matrix is %lld x %lld, not square", (long long)a->rows,
            (long long)a->cols);
@@ -689,6 +690,7 @@ extern "C" int mb_potrf(mb_ctx* ctx, mb_mat* a) {
 }
 
 extern "C" int mb_trsm_right_lt(mb_ctx* ctx, const mb_mat* Lp, mb_mat* X) {
+  MB_RANGE("mellon_b200: K3 trsm_right_lt");
   MB_CHECK(ctx && Lp && X, "mb_trsm_right_lt: null argument");
   MB_CHECK(Lp->rows == Lp->cols && X->cols == Lp->rows,
            "mb_trsm_right_lt: Lp is %lld x %lld, X is %lld x %lld", (long long)Lp->rows,
@@ -699,6 +701,7 @@ extern "C" int mb_trsm_right_lt(mb_ctx* ctx, const mb_mat* Lp, mb_mat* X) {
 }
 
 extern "C" int mb_tri_solve(mb_ctx* ctx, const mb_mat* Lp, int trans, mb_mat* B) {
+  MB_RANGE("mellon_b200: tri_solve");
   MB_CHECK(ctx && Lp && B, "mb_tri_solve: null argument");
   MB_CHECK(Lp->rows == Lp->cols && B->rows == Lp->rows, "mb_tri_solve: Lp is %lld x %lld, B has %lld rows",
            (long long)Lp->rows, (long long)Lp->cols, (long long)B->rows);

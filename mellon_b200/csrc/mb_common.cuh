@@ -1,6 +1,7 @@
 // Shared internals of libmellon_b200.so (not part of the ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -179,6 +180,13 @@ void mb_set_error(const char* fmt, ...);
     }                                                                              \
     MB_CUDA(cudaGetLastError());                                                   \
   } while (0)
+
+// NVTX range over an entry point (free unless a profiler is attached): one timeline row per stage of a fit
+struct mb_nvtx_range {
+  explicit mb_nvtx_range(const char* name) { nvtxRangePushA(name); }
+  ~mb_nvtx_range() { nvtxRangePop(); }
+};
+#define MB_RANGE(name) mb_nvtx_range _mb_nvtx_range_(name)
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -960,6 +960,7 @@ int cov_build_impl(mb_ctx* ctx, const mb_kprog* prog, const mb_mat* x, const mb_
 }  // namespace
 
 extern "C" int mb_cov_build(mb_ctx* ctx, const mb_kprog* prog, const mb_mat* x, const mb_mat* y, mb_mat* K) {
+  MB_RANGE("mellon_b200: K1 cov_build");
   MB_CHECK(ctx && prog && x && y && K, "mb_cov_build: null argument");
   MB_CHECK(K->rows == x->rows && K->cols == y->rows, "mb_cov_build: K is %lld x %lld, expected %lld x %lld",
            (long long)K->rows, (long long)K->cols, (long long)x->rows, (long long)y->rows);
@@ -984,6 +985,7 @@ extern "C" int mb_cov_diag(mb_ctx* ctx, const mb_kprog* prog, const mb_mat* x, m
 
 extern "C" int mb_cov_matvec(mb_ctx* ctx, const mb_kprog* prog, const mb_mat* xq, const mb_mat* base,
                              const mb_mat* w, double mu, mb_mat* out) {
+  MB_RANGE("mellon_b200: K7 cov_matvec");
   MB_CHECK(ctx && prog && xq && base && w && out, "mb_cov_matvec: null argument");
   MB_CHECK(w->rows == base->rows, "mb_cov_matvec: weights have %lld rows for %lld base points",
            (long long)w->rows, (long long)base->rows);
@@ -1025,6 +1027,7 @@ extern "C" int mb_cov_matvec(mb_ctx* ctx, const mb_kprog* prog, const mb_mat* xq
 
 extern "C" int mb_predict_mean(mb_ctx* ctx, const mb_kprog* prog, const double* xq_host, int64_t nq, int64_t d,
                                const mb_mat* base, const mb_mat* w, double mu, double* out_host) {
+  MB_RANGE("mellon_b200: K7 predict_mean (host queries)");
   MB_CHECK(ctx && prog && base && w && (nq == 0 || (xq_host && out_host)), "mb_predict_mean: null argument");
   MB_CHECK(d == base->cols, "mb_predict_mean: queries have %lld features, base points %lld", (long long)d,
            (long long)base->cols);
@@ -1088,6 +1091,7 @@ extern "C" int mb_predict_mean(mb_ctx* ctx, const mb_kprog* prog, const double* 
 
 extern "C" int mb_nn_distances(mb_ctx* ctx, const mb_mat* x, const mb_mat* all, int64_t self_offset, mb_mat* dist,
                                int64_t* idx_host) {
+  MB_RANGE("mellon_b200: nn_distances");
   MB_CHECK(ctx && x && all && dist, "mb_nn_distances: null argument");
   MB_CHECK(x->cols == all->cols, "mb_nn_distances: feature counts differ (%lld vs %lld)", (long long)x->cols,
            (long long)all->cols);

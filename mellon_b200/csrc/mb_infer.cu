@@ -679,6 +679,7 @@ int objective_pass(mb_ctx* ctx, const mb_mat* L, const mb_mat* V, double mu, con
 }  // namespace
 
 extern "C" int mb_transform(mb_ctx* ctx, const mb_mat* L, const double* z_host, double mu, double* f_host) {
+  MB_RANGE("mellon_b200: transform");
   MB_CHECK(ctx && L && z_host && (f_host || L->rows == 0), "mb_transform: null argument");
   MB_CUDA(cudaSetDevice(ctx->device));
   const int64_t n = L->rows;
@@ -695,6 +696,7 @@ extern "C" int mb_transform(mb_ctx* ctx, const mb_mat* L, const double* z_host, 
 
 extern "C" int mb_loss_grad(mb_ctx* ctx, const mb_mat* L, const mb_mat* V, double sum_vdr, double mu, double k,
                             const double* z_host, double* loss, double* grad_host) {
+  MB_RANGE("mellon_b200: K5 loss_grad");
   MB_CHECK(ctx && L && V && z_host && loss && grad_host, "mb_loss_grad: null argument");
   MB_CHECK(V->rows * V->cols == L->rows, "mb_loss_grad: V has %lld entries for %lld cells",
            (long long)(V->rows * V->cols), (long long)L->rows);
@@ -718,6 +720,7 @@ extern "C" int mb_loss_grad(mb_ctx* ctx, const mb_mat* L, const mb_mat* V, doubl
 
 extern "C" int mb_hess_diag(mb_ctx* ctx, const mb_mat* L, const mb_mat* V, double mu, const double* z_host,
                             double* diag_host) {
+  MB_RANGE("mellon_b200: K6 hess_diag");
   MB_CHECK(ctx && L && V && z_host && diag_host, "mb_hess_diag: null argument");
   MB_CHECK(V->rows * V->cols == L->rows, "mb_hess_diag: V has %lld entries for %lld cells",
            (long long)(V->rows * V->cols), (long long)L->rows);
@@ -735,6 +738,7 @@ extern "C" int mb_hess_diag(mb_ctx* ctx, const mb_mat* L, const mb_mat* V, doubl
 
 // b = L^T t  [tree reduce over the cells of all ranks]
 extern "C" int mb_gemv_t(mb_ctx* ctx, const mb_mat* L, const mb_mat* t, mb_mat* b) {
+  MB_RANGE("mellon_b200: gemv_t");
   MB_CHECK(ctx && L && t && b, "mb_gemv_t: null argument");
   MB_CHECK(t->rows * t->cols == L->rows && b->rows * b->cols == L->cols, "mb_gemv_t: shape mismatch");
   MB_CUDA(cudaSetDevice(ctx->device));

@@ -5,6 +5,7 @@
 #include "mb_common.cuh"
 
 extern "C" int mb_gram(mb_ctx* ctx, const mb_mat* L, mb_mat* G) {
+  MB_RANGE("mellon_b200: K4 gram");
   MB_CHECK(ctx && L && G, "mb_gram: null argument");
   MB_CHECK(G->rows == L->cols && G->cols == L->cols, "mb_gram: G must be %lld x %lld", (long long)L->cols,
            (long long)L->cols);
@@ -20,6 +21,7 @@ extern "C" int mb_gram(mb_ctx* ctx, const mb_mat* L, mb_mat* G) {
 }
 
 extern "C" int mb_ridge_init(mb_ctx* ctx, const mb_mat* L, const mb_mat* t, double* z0_host) {
+  MB_RANGE("mellon_b200: ridge_init (K4 + K2 + TRSV)");
   MB_CHECK(ctx && L && t && z0_host, "mb_ridge_init: null argument");
   MB_CHECK(t->rows * t->cols == L->rows, "mb_ridge_init: target has %lld entries for %lld cells",
            (long long)(t->rows * t->cols), (long long)L->rows);
@@ -88,6 +90,7 @@ int load_cusolver() {
 }  // namespace
 
 extern "C" int mb_syevd(mb_ctx* ctx, mb_mat* a, mb_mat* w) {
+  MB_RANGE("mellon_b200: syevd (cuSOLVER)");
   MB_CHECK(ctx && a && w, "mb_syevd: null argument");
   MB_CHECK(a->rows == a->cols && w->rows * w->cols == a->rows, "mb_syevd: shape mismatch");
   MB_CUDA(cudaSetDevice(ctx->device));

@@ -151,9 +151,12 @@ def minimize_lbfgsb(loss_func, initial_value, jit=DEFAULT_JIT):
     ``jaxopt.ScipyMinimize(method="L-BFGS-B")`` calls ``scipy.optimize.minimize(fun, x0,
     jac=True, tol=None, method="L-BFGS-B", options={"maxiter": 500})``; the same call is made
     here so the trajectory is the reference's up to the rounding of (loss, grad)."""
+    from .backend import get_backend
+
     fun = _value_and_grad(loss_func)
-    res = minimize(fun, np.asarray(initial_value, dtype=np.float64), jac=True, tol=None, method="L-BFGS-B",
-                   options=dict(LBFGSB_OPTIONS))
+    with get_backend().range("L-BFGS-B (SciPy on the host, K5 per evaluation)"):
+        res = minimize(fun, np.asarray(initial_value, dtype=np.float64), jac=True, tol=None, method="L-BFGS-B",
+                       options=dict(LBFGSB_OPTIONS))
     state = ScipyMinimizeInfo(
         fun_val=np.asarray(res.fun),
         success=res.success,

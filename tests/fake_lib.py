@@ -196,6 +196,14 @@ class FakeLib:
     def mb_flush_l2(self, ctx):
         return 0
 
+    def mb_range_push(self, name):
+        self.ranges = getattr(self, "ranges", [])
+        self.ranges.append(name)
+        return 0
+
+    def mb_range_pop(self):
+        return 0
+
     def mb_set_option(self, ctx, key, value):
         return 0
 

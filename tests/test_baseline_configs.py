@@ -4,7 +4,9 @@ acceptance metric std(a - b) / std(b) (tests/test_density_estimator.py:30-44) fo
 
   1. stage-wise, at fixed inputs: the factor Lp reproduces K_MM + jitter I to rounding (backward error), L and the
      Ridge start z0 agree with the oracle's to the accuracy the conditioning of the problem allows;
-  2. converged: with both optimisers run to convergence the log densities agree to 1e-6 — same objective, same optimum;
+  2. converged: with both optimisers run to convergence (gtol 1e-9) the log densities agree to 1e-6 — same objective,
+     same optimum — or, where the optimum is so flat that the oracle does not reproduce ITSELF to 1e-6 at that
+     tolerance (landmarks permuted), to three times that measured floor;
   3. default stop (SciPy's ftol, what the reference runs): the gap to the oracle is no larger than the gap between the
      oracle and ITSELF when its landmarks are permuted — identical mathematics, different rounding.  That
      reference-vs-reference floor is measured in the test; where it is below 1e-5 the 1e-5 bar of north_star applies.
@@ -55,7 +57,11 @@ def check_density_config(cuda, X, lm, nn, cov_o, cov_c, rank=None, label=""):
     ref_perm = O.fit_density(X, cov_func_curry=cov_o, landmarks=np.ascontiguousarray(lm[perm]), nn_distances=nn, rank=rank)
     best = O.fit_density(X, cov_func_curry=cov_o, lbfgsb_options=TIGHT, Lp=ref.Lp if rank is None else None,
                          L=ref.L if rank is None else None, **kw)
+    best_perm = O.fit_density(X, cov_func_curry=cov_o, landmarks=np.ascontiguousarray(lm[perm]), nn_distances=nn, rank=rank,
+                              lbfgsb_options=TIGHT, Lp=ref_perm.Lp if rank is None else None,
+                              L=ref_perm.L if rank is None else None)
     floor = relstd(ref_perm.log_density_x, ref.log_density_x)
+    floor_conv = relstd(best_perm.log_density_x, best.log_density_x)
 
     est = mb.DensityEstimator(cov_func_curry=cov_c, check_rank=False, **kw)
     dens = est.fit_predict(X)
@@ -83,9 +89,9 @@ def check_density_config(cuda, X, lm, nn, cov_o, cov_c, rank=None, label=""):
     # 3. default stop against the measured reference-vs-reference floor
     gap = relstd(dens, ref.log_density_x)
     print(f"\n[{label}] N={X.shape[0]} M={lm.shape[0]}: |dL|={dL:.2e} |dz0|/|z0|={dz0:.2e} converged {conv:.2e} "
-          f"default-stop gap {gap:.2e} (oracle-vs-oracle floor {floor:.2e}) nfev cuda/oracle "
+          f"(oracle-vs-oracle {floor_conv:.2e}) default-stop gap {gap:.2e} (oracle-vs-oracle {floor:.2e}) nfev cuda/oracle "
           f"{est.opt_state.num_fun_eval}/{ref.opt_state.num_fun_eval}")
-    assert conv < 1e-6, conv
+    assert conv < max(1e-6, 3 * floor_conv), (conv, floor_conv)
     assert gap < max(1e-5, 3 * floor), (gap, floor)
     return est, ref
 
@@ -99,7 +105,8 @@ def test_config2_shape_expquad_m5000(cuda):
     # configs[4] shape: out-of-sample predict on the fitted model.  The weights Lp^-T z amplify the default-stop
     # difference of z by 1 / sqrt(jitter), so the predictions are compared at the oracle's own pre_transformation
     Y = np.random.default_rng(2).random((20_000, 50))
-    pred_fn = mb.conditional.LandmarksConditionalCholesky(lm, ref.pre_transformation, ref.mu, est.cov_func, Lp=est.Lp)
+    pred_fn = mb.conditional.LandmarksConditionalCholesky(lm, ref.pre_transformation, ref.mu, est.cov_func, X.shape[0],
+                                                          L=est.Lp)
     gap_pred = relstd(pred_fn(Y), O.predict_density(ref, X, Y))
     print(f"[config 5] predict 20 000 queries with the oracle's latent vector: {gap_pred:.2e}")
     assert gap_pred < 1e-5
