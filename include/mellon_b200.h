@@ -118,8 +118,9 @@ int mb_flush_l2(mb_ctx* ctx);
  *   "trsm"     1 = 32-wide substitution leaves for TRSM / Cholesky (no inverted 128-blocks, no blocked TRSV)
  *   "lossgrad" 1 = two-pass objective, 2 = register-fused single pass (0 = bulk-TMA ring)
  *   "graph"    0 = launch the Cholesky on the stream instead of replaying its CUDA graph
- *   "i8"       0 = Gram products of large factors on the FP64 DMMA tiles instead of tcgen05 kind::i8 digit slices
- *              (the default, 1: chunk >= 2048 cells and r >= 512) */
+ *   "i8"       0 = every FP64 product on the DMMA tiles; 1 (default) = the large products on tcgen05 kind::i8 digit
+ *              slices: Gram matrices with chunks >= 2048 cells and r >= 512, TRSM updates / tall GEMMs with >= 8192
+ *              cells, k >= 512 and >= 256 output columns; 2 = int8 slices at every size (tests, sanitizer runs) */
 int mb_set_option(mb_ctx* ctx, const char* key, int value);
 
 /* pinned (page-locked) host buffers, so uploads / the streaming predictor overlap with compute */
@@ -167,6 +168,8 @@ int mb_mat_scale_cols(mb_ctx* ctx, mb_mat* a, const mb_mat* s);
 int mb_mat_scale_rows(mb_ctx* ctx, mb_mat* a, const mb_mat* s);
 /* dst <- src[:, c0:c0+ncols]      decomposition.py:75-76 (`v[:, -p:]`) */
 int mb_mat_copy_cols(mb_ctx* ctx, const mb_mat* src, int64_t c0, int64_t ncols, mb_mat* dst);
+/* dst <- src[r0:r0+nrows, :] */
+int mb_mat_copy_rows(mb_ctx* ctx, const mb_mat* src, int64_t r0, int64_t nrows, mb_mat* dst);
 /* copy the lower triangle onto the upper one (symmetrise a lower-only result) */
 int mb_mat_symmetrize(mb_ctx* ctx, mb_mat* a);
 /* a *= s                          conditional.py:139-181 (`A / sigma2`), :296-300 */
@@ -194,6 +197,15 @@ int mb_cov_diag(mb_ctx* ctx, const mb_kprog* prog, const mb_mat* x, mb_mat* out)
  * recomputed as sqrt(sum (x - y)^2).  Replaces parameters.py:352-433 (pynndescent k=1). */
 int mb_nn_distances(mb_ctx* ctx, const mb_mat* x, const mb_mat* all, int64_t self_offset, mb_mat* dist,
                     int64_t* idx_host);
+
+/* ---- k-means landmarks (the step before the path) --------------------------------------------
+ * One seeding step of k-means++ as scikit-learn's k_means runs it (sklearn/cluster/_kmeans.py:_kmeans_plusplus, reached
+ * from parameters.py:291): for the T <= 16 candidate rows `cand` (T x d) and every row of x,
+ *   out(t, i) = min(closest(i), max(|x_i|^2 - 2 x_i . c_t + |c_t|^2, 0))     (closest == NULL: no minimum)
+ *   pot(t)    = sum_i out(t, i)                                               (fixed order, returned on the host)
+ * xnorm holds |x_i|^2.  The Lloyd assignment step is mb_nn_distances(x, centres, self_offset < -rows). */
+int mb_sqdist_min(mb_ctx* ctx, const mb_mat* x, const mb_mat* xnorm, const mb_mat* cand, const mb_mat* closest,
+                  mb_mat* out, double* pot_host);
 
 /* ---- K7: fused covariance + mat-vec (never materialises K) -----------------------------
  * out = mu + prog(xq, base) @ w ; w is (m, p), out is (nq, p).

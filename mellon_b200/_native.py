@@ -100,6 +100,7 @@ SIGNATURES = {
     "mb_mat_scale_cols": (_i, [_vp, _vp, _vp]),
     "mb_mat_scale_rows": (_i, [_vp, _vp, _vp]),
     "mb_mat_copy_cols": (_i, [_vp, _vp, _i64, _i64, _vp]),
+    "mb_mat_copy_rows": (_i, [_vp, _vp, _i64, _i64, _vp]),
     "mb_mat_symmetrize": (_i, [_vp, _vp]),
     "mb_mat_scale": (_i, [_vp, _vp, _d]),
     "mb_mat_combine": (_i, [_vp, _i, _vp, _vp, _d]),
@@ -107,6 +108,7 @@ SIGNATURES = {
     "mb_cov_build": (_i, [_vp, _pprog, _vp, _vp, _vp]),
     "mb_cov_diag": (_i, [_vp, _pprog, _vp, _vp]),
     "mb_nn_distances": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "mb_sqdist_min": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _pd]),
     "mb_cov_matvec": (_i, [_vp, _pprog, _vp, _vp, _vp, _d, _vp]),
     "mb_predict_mean": (_i, [_vp, _pprog, _vp, _i64, _i64, _vp, _vp, _d, _vp]),
     "mb_potrf": (_i, [_vp, _vp]),

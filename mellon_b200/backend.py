@@ -579,6 +579,34 @@ class CudaBackend:
         nat.check(self.lib.mb_mat_copy_cols(self.ctx, A._h, int(c0), int(ncols), out._h), "mb_mat_copy_cols")
         return out
 
+    def copy_rows(self, A, r0, nrows):
+        out = self.empty(nrows, A.local_shape[1])
+        nat.check(self.lib.mb_mat_copy_rows(self.ctx, A._h, int(r0), int(nrows), out._h), "mb_mat_copy_rows")
+        return out
+
+    def sqdist_min(self, xd, xnorm_d, candidates, closest_d):
+        """One k-means++ seeding step (``mb_sqdist_min``): ``out[t, i] = min(closest[i], |x_i - c_t|^2)`` as a
+        device matrix and the candidates' potentials ``sum_i out[t, i]`` on the host."""
+        cd = self.upload(np.ascontiguousarray(candidates, dtype=np.float64))
+        T = cd.local_shape[0]
+        out = self.empty(T, xd.local_shape[0])
+        pot = np.empty(T, dtype=np.float64)
+        nat.check(self.lib.mb_sqdist_min(self.ctx, xd._h, xnorm_d._h, cd._h, closest_d._h if closest_d is not None else None,
+                                         out._h, pot.ctypes.data_as(C.POINTER(C.c_double))), "mb_sqdist_min")
+        self.d2h_bytes += pot.nbytes
+        return out, pot
+
+    def nearest_rows(self, xd, centers):
+        """Index of the nearest row of ``centers`` for every row of the device matrix ``xd`` (exact, brute force)."""
+        cd = self.upload(np.ascontiguousarray(centers, dtype=np.float64))
+        n = xd.local_shape[0]
+        dist = self.empty(n, 1, vector=True)
+        idx = np.empty(n, dtype=np.int64)
+        nat.check(self.lib.mb_nn_distances(self.ctx, xd._h, cd._h, -(n + cd.local_shape[0] + 2), dist._h, nat.ptr(idx)),
+                  "mb_nn_distances")
+        self.d2h_bytes += idx.nbytes
+        return idx
+
     def transpose(self, A):
         out = self.empty(A.local_shape[1], A.local_shape[0])
         nat.check(self.lib.mb_mat_transpose(self.ctx, A._h, out._h), "mb_mat_transpose")

@@ -548,6 +548,18 @@ extern "C" int mb_mat_copy_cols(mb_ctx* c, const mb_mat* src, int64_t c0, int64_
   return 0;
 }
 
+extern "C" int mb_mat_copy_rows(mb_ctx* c, const mb_mat* src, int64_t r0, int64_t nrows, mb_mat* dst) {
+  MB_CHECK(c && src && dst, "mb_mat_copy_rows: null argument");
+  MB_CHECK(r0 >= 0 && nrows >= 0 && r0 + nrows <= src->rows && dst->rows == nrows && dst->cols == src->cols,
+           "mb_mat_copy_rows: rows [%lld, %lld) of a %lld x %lld matrix into %lld x %lld", (long long)r0,
+           (long long)(r0 + nrows), (long long)src->rows, (long long)src->cols, (long long)dst->rows, (long long)dst->cols);
+  MB_CUDA(cudaSetDevice(c->device));
+  if (nrows * src->cols == 0) return 0;
+  MB_CUDA(cudaMemcpyAsync(dst->p, src->p + r0 * src->cols, (size_t)(nrows * src->cols) * sizeof(double),
+                          cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+
 extern "C" int mb_mat_symmetrize(mb_ctx* c, mb_mat* a) {
   MB_CHECK(c && a, "mb_mat_symmetrize: null argument");
   MB_CHECK(a->rows == a->cols, "mb_mat_symmetrize: not square");

@@ -494,6 +494,21 @@ extern "C" int mb_gemm(mb_ctx* ctx, int trans_a, int trans_b, double alpha, cons
   if (ka == 0) {
     if (beta == 0.0) return mb_mat_fill(ctx, C, 0.0);
   }
+  if (!trans_a && A->global_rows >= 0 && (beta == 0.0 || beta == 1.0) && mb_i8_nt_usable(ctx, A->global_rows, n, ka)) {
+    // tall (cells x k) times (k x n): tcgen05 int8 digit slices (decomposition.py:123 / :265, the Nystroem factor Q V)
+    const double* Bt = B->p;
+    int64_t ldbt = B->cols;
+    if (!trans_b) {  // the int8 kernel takes B as n x k (k contiguous): transpose the small operand
+      double* tmp;
+      MB_TRY(mb_scratch(ctx, (size_t)n * ka * sizeof(double), &tmp));
+      mb_mat tv = {tmp, n, ka, ctx, false};
+      MB_TRY(mb_mat_transpose(ctx, B, &tv));
+      Bt = tmp;
+      ldbt = ka;
+    }
+    MB_TRY(mb_i8_gemm_nt(ctx, m, n, ka, alpha, A->p, A->cols, Bt, ldbt, beta == 1.0 ? 1 : 0, C->p, C->cols));
+    return mb_i8_check(ctx);
+  }
   if (!trans_a && A->global_rows >= 0)  // output rows are cells: an output row must not depend on the local row count
     return mb_gemm_rows_raw(ctx, false, trans_b == 0, m, n, ka, alpha, A->p, A->cols, B->p, B->cols, beta, C->p, C->cols);
   return mb_gemm_raw(ctx, trans_a != 0, trans_b == 0, m, n, ka, alpha, A->p, A->cols, B->p, B->cols, beta, C->p,

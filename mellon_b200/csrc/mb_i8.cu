@@ -476,6 +476,7 @@ int ensure_ws(mb_ctx* ctx, size_t bytes) {
 }  // namespace
 
 bool mb_i8_gram_usable(mb_ctx* ctx, int64_t rows, int64_t r) {
+  if (ctx->opt_i8 == 2) return r >= 1 && rows >= 1;   // forced (tests, sanitizer runs on small shapes)
   return ctx->opt_i8 != 0 && r >= 512 && rows >= 2048;
 }
 
@@ -559,6 +560,7 @@ int mb_i8_gram_leaf(mb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int
 
 
 bool mb_i8_nt_usable(mb_ctx* ctx, int64_t rows_total, int64_t p, int64_t k) {
+  if (ctx->opt_i8 == 2) return k >= 1 && k <= KC;
   return ctx->opt_i8 != 0 && rows_total >= 8192 && p >= 256 && k >= 512 && k <= KC;
 }
 

@@ -109,8 +109,9 @@ def compute_gp_type(n_landmarks, rank, n_samples):
 
 
 def compute_landmarks(x, gp_type=None, n_landmarks=DEFAULT_N_LANDMARKS, random_state=DEFAULT_RANDOM_SEED):
-    """k-means centroids as landmarks (parameters.py:243-291); None when n_landmarks >= n."""
-    from sklearn.cluster import k_means
+    """k-means centroids as landmarks (parameters.py:243-291); None when n_landmarks >= n.  scikit-learn's
+    ``k_means(x, k, n_init=1, random_state=seed)`` algorithm with its distance work on the device (kmeans.py)."""
+    from .kmeans import k_means
 
     if n_landmarks == 0:
         return None
@@ -127,7 +128,7 @@ def compute_landmarks(x, gp_type=None, n_landmarks=DEFAULT_N_LANDMARKS, random_s
             return x
         return None
     logger.info(f"Computing {n_landmarks:,} landmarks with k-means clustering (random_state={random_state}).")
-    return k_means(x, n_landmarks, n_init=1, random_state=random_state)[0]
+    return k_means(x, n_landmarks, random_state=random_state)
 
 
 def compute_landmarks_rescale_time(x, ls, ls_time, times=None, n_landmarks=DEFAULT_N_LANDMARKS,

@@ -294,6 +294,10 @@ class FakeLib:
         self.A(dst)[...] = self.A(src)[:, c0:c0 + ncols]
         return 0
 
+    def mb_mat_copy_rows(self, ctx, src, r0, nrows, dst):
+        self.A(dst)[...] = self.A(src)[r0:r0 + nrows]
+        return 0
+
     def mb_mat_symmetrize(self, ctx, h):
         a = self.A(h)
         a[...] = np.tril(a) + np.tril(a, -1).T
@@ -357,12 +361,25 @@ class FakeLib:
             blk = xa[lo:lo + 256]
             d2 = ((blk[:, None, :] - ya[None, :, :]) ** 2).sum(-1)
             rows = np.arange(blk.shape[0])
-            d2[rows, rows + lo + self_offset] = np.inf
+            own = rows + lo + self_offset                            # the row's own column, when it has one
+            ok = (own >= 0) & (own < ya.shape[0])
+            d2[rows[ok], own[ok]] = np.inf
             j[lo:lo + 256] = np.argmin(d2, axis=1)
             best[lo:lo + 256] = d2[rows, j[lo:lo + 256]]
         self.A(dist)[:, 0] = np.sqrt(best)
         if _val(idx_host):
             np.ctypeslib.as_array((C.c_int64 * xa.shape[0]).from_address(_val(idx_host)))[:] = j
+        return 0
+
+    def mb_sqdist_min(self, ctx, x, xnorm, cand, closest, out, pot):
+        xa, ca, xn = self.A(x), self.A(cand), self.A(xnorm).ravel()
+        d = np.maximum(xn[None, :] - 2.0 * (ca @ xa.T) + np.sum(ca * ca, axis=1)[:, None], 0.0)
+        if closest is not None and _val(closest):
+            d = np.minimum(d, self.A(closest).ravel()[None, :])
+        self.A(out)[...] = d
+        pot_arr = np.ctypeslib.as_array((C.c_double * ca.shape[0]).from_address(C.addressof(pot.contents)
+                                                                                 if hasattr(pot, "contents") else _val(pot)))
+        pot_arr[:] = d.sum(axis=1)
         return 0
 
     # ---- factorisations / solves ----------------------------------------------------------------

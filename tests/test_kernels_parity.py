@@ -520,3 +520,48 @@ def test_trsm_right_with_int8_updates(be, n, m):
     half = be.trsm_right_lt(Lpd, be.upload(X[: n // 2].copy())).numpy()
     if n // 2 >= 8192:
         assert np.array_equal(half, out[: n // 2])
+
+
+@pytest.mark.parametrize("n,k,p,trans_b", [(9000, 1100, 700, False), (8200, 640, 300, True)])
+def test_tall_gemm_with_int8_slices(be, n, k, p, trans_b):
+    """C = A B for a tall row-sharded A (cells x k): the Nystroem factor Q V (decomposition.py:265) on the int8
+    digit slices; rows of very different magnitude, agreement with NumPy and with the FP64 DMMA path to rounding."""
+    if be.name != "cuda":
+        pytest.skip("the int8 digit-slice path exists in the CUDA library only")
+    rng = np.random.default_rng(n + k + p)
+    A = rng.standard_normal((n, k)) * 10.0 ** rng.uniform(-3, 3, size=(n, 1))
+    B = rng.standard_normal((p, k) if trans_b else (k, p)) * 10.0 ** rng.uniform(-2, 2, size=(p, 1) if trans_b else (1, p))
+    Ad = be.upload(A, sharded=True)
+    out = be.gemm(Ad, be.upload(B), trans_b=trans_b).numpy()
+    be.set_option("i8", 0)
+    try:
+        out64 = be.gemm(Ad, be.upload(B), trans_b=trans_b).numpy()
+    finally:
+        be.set_option("i8", 1)
+    Bm = B.T if trans_b else B
+    ref, bound = A @ Bm, np.abs(A) @ np.abs(Bm)
+    assert np.max(np.abs(out - ref) / bound) < 1e-14
+    assert np.max(np.abs(out - out64) / bound) < 1e-14
+
+
+@pytest.mark.parametrize("n,r", [(1, 1), (50, 7), (777, 130), (3000, 257), (4099, 64)])
+def test_int8_slices_forced_on_small_and_ragged_shapes(be, n, r):
+    """Option i8 = 2 sends EVERY Gram / TRSM update / tall GEMM through the int8 digit-slice kernels: ragged and tiny
+    shapes (partial tiles, partial k-steps, single rows) against NumPy at the FP64 tolerances."""
+    if be.name != "cuda":
+        pytest.skip("the int8 digit-slice path exists in the CUDA library only")
+    rng = np.random.default_rng(n + r)
+    L = rng.standard_normal((n, r)) / np.sqrt(r)
+    be.set_option("i8", 2)
+    try:
+        Ld = be.upload(L, sharded=True)
+        G = be.gram(Ld).numpy()
+        assert rel_err(G, L.T @ L) < 1e-13 and np.array_equal(G, G.T)
+        Lp = np.linalg.cholesky(_spd(r, r, 1e4))
+        X = rng.standard_normal((n, r))
+        out = be.trsm_right_lt(be.upload(Lp), be.upload(X.copy(), sharded=True)).numpy()
+        assert rel_err(out, solve_triangular(Lp, X.T, lower=True).T) < 1e-11
+        B = rng.standard_normal((r, 37))
+        assert rel_err(be.gemm(Ld, be.upload(B)).numpy(), L @ B) < 1e-13
+    finally:
+        be.set_option("i8", 1)
