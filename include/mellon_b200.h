@@ -132,6 +132,10 @@ int mb_comm_unique_id(unsigned char* out128);
 int mb_comm_init(mb_ctx* ctx, const unsigned char* id128, int rank, int world);
 int mb_comm_destroy(mb_ctx* ctx);
 int mb_comm_info(mb_ctx* ctx, int* rank, int* world);
+/* on != 0: until switched off this rank works ALONE although a communicator is attached — matrices marked as rows
+ * [0, n) of n are summed locally, nothing is exchanged.  Reproduces the one-GPU computation inside a multi-GPU job
+ * (bench.py and tools/check_multi_gpu.py compare its bits with the sharded result). */
+int mb_comm_solo(mb_ctx* ctx, int on);
 /* Row block [*row_lo, *row_hi) of rank `rank` of `world` for a cell axis of `global_rows` rows: whole chunks of
  * *chunk_rows = ceil(global_rows / 32) rows, chunks [32 rank / world, 32 (rank + 1) / world).  Pure function. */
 int mb_row_block(int64_t global_rows, int rank, int world, int64_t* row_lo, int64_t* row_hi, int64_t* chunk_rows);

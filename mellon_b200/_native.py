@@ -82,6 +82,7 @@ SIGNATURES = {
     "mb_comm_unique_id": (_i, [C.c_char_p]),
     "mb_comm_init": (_i, [_vp, C.c_char_p, _i, _i]),
     "mb_comm_destroy": (_i, [_vp]),
+    "mb_comm_solo": (_i, [_vp, _i]),
     "mb_comm_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
     "mb_row_block": (_i, [_i64, _i, _i, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "mb_mat_set_shard": (_i, [_vp, _i64, _i64]),

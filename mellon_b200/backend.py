@@ -185,15 +185,18 @@ class CudaBackend:
     @contextlib.contextmanager
     def replicated(self):
         """Inside the block this rank works ALONE on whole matrices even though a communicator is attached:
-        nothing is sharded, nothing is marked as a row block, so the library sums over local rows only.  Used to
+        nothing is sharded and the library is told to work solo (``mb_comm_solo``), so every matrix is the whole matrix
+        and every path is the one a single-GPU process takes.  Used to
         reproduce the one-GPU result inside a multi-GPU job (bench.py / tools/check_multi_gpu.py compare its bits
         with the sharded result: the reduction tree makes them identical)."""
-        saved = (self.rank, self.world, getattr(self, "_replicated", False))
-        self.rank, self.world, self._replicated = 0, 1, True
+        saved = (self.rank, self.world)
+        nat.check(self.lib.mb_comm_solo(self.ctx, 1), "mb_comm_solo")
+        self.rank, self.world = 0, 1
         try:
             yield self
         finally:
-            self.rank, self.world, self._replicated = saved
+            self.rank, self.world = saved
+            nat.check(self.lib.mb_comm_solo(self.ctx, 0), "mb_comm_solo")
 
     # -- bookkeeping --------------------------------------------------------------------------
     def sync(self):
@@ -272,7 +275,7 @@ class CudaBackend:
         """Uninitialised device matrix; with ``global_rows`` it is this rank's row block of a matrix whose
         cell axis is sharded, and the library is told so (sums over its rows then span all ranks)."""
         d = DeviceArray(self, self._alloc(rows, cols), (rows, cols), global_rows, row_lo, vector)
-        if global_rows is not None and not getattr(self, "_replicated", False):
+        if global_rows is not None:
             nat.check(self.lib.mb_mat_set_shard(d._h, int(global_rows), int(row_lo)), "mb_mat_set_shard")
         return d
 

@@ -215,6 +215,8 @@ extern "C" int mb_set_option(mb_ctx* c, const char* key, int value) {
   else if (!strcmp(key, "graph")) c->opt_graph = value;
   else if (!strcmp(key, "lossgrad")) c->opt_lossgrad = value;
   else if (!strcmp(key, "i8")) c->opt_i8 = value;
+  else if (!strcmp(key, "cov_i8")) c->opt_cov_i8 = value;
+  else if (!strcmp(key, "i8_issuers")) c->opt_i8_issuers = value;
   else MB_CHECK(false, "mb_set_option: unknown key %s", key);
   return 0;
 }

@@ -57,6 +57,9 @@ int mb_axpy_raw(mb_ctx* ctx, double* dst, const double* src, int64_t count);
 bool mb_i8_gram_usable(mb_ctx* ctx, int64_t rows, int64_t r);
 int mb_i8_gram_leaf(mb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t r, double* out);
 int mb_i8_check(mb_ctx* ctx);
+// K1 on int8 digit slices (mb_cov_i8.cu); *done = false: shape / kind outside that kernel
+int mb_cov_i8_build(mb_ctx* ctx, int kind, double c, const mb_mat* x, const mb_mat* y, const int* dims_host, int d,
+                    double* out, int64_t ldo, bool* done);
 // C = beta C + alpha A B^T on int8 digit slices (A: n x k, B: p x k row-major; beta 0 or 1); rows_total: the GLOBAL
 // number of rows of the row-sharded operand (the path is chosen from it, not from the local row count)
 bool mb_i8_nt_usable(mb_ctx* ctx, int64_t rows_total, int64_t p, int64_t k);
@@ -108,10 +111,13 @@ struct mb_ctx {
   int64_t i8_tiles_r = -1;
   int i8_ntiles = 0;
   int* i8_status = nullptr;
+  int opt_cov_i8 = 1;    // 1 = K1 of one exponential-family leaf on tcgen05 int8 digit slices (large shapes), 2 = always, 0 = DMMA kernel
+  int opt_i8_issuers = 4;  // MMA-issuing warps of the int8 GEMM kernels (1, 2 or 4)
   int opt_i8 = 1;        // 1 = Gram products of large factors on tcgen05 kind::i8 digit slices, 0 = FP64 DMMA tiles
   // NCCL
   void* comm = nullptr;
   int rank = 0, world = 1;
+  bool solo = false;     // mb_comm_solo: behave as a single rank although a communicator is attached
   // options
   int opt_gemm = 0;      // 0 = DMMA tiles (default), 1 = DFMA register tiles
   int opt_cov = 0;       // 0 = DMMA tile kernel (exp-family leaf) else 1; 1 = DFMA register-tile kernel; 2 = general kernel

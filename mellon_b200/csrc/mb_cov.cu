@@ -948,6 +948,25 @@ int launch_general(mb_ctx* ctx, const Plan& plan, int64_t n, int64_t m, double* 
 
 int cov_build_impl(mb_ctx* ctx, const mb_kprog* prog, const mb_mat* x, const mb_mat* y, double* out, int64_t ldo) {
   if (x->rows == 0 || y->rows == 0) return 0;
+  // tensor-core route (mb_cov_i8.cu): ONE exponential-family leaf, cells x landmarks (x != y), large shapes, D <= 64
+  if (ctx->opt_cov == 0 && ctx->opt_cov_i8 != 0 && x->p != y->p) {
+    Program pr;
+    MB_TRY(parse_program(prog, x->cols, &pr));
+    if (pr.leaves.size() == 1 && pr.n_ops == 1) {
+      const Leaf& lf = pr.leaves[0];
+      const double sc = mma_scale(lf);
+      if (sc > 0.0) {
+        bool done = false;
+        const int d0 = lf.all_dims ? (int)x->cols : (int)lf.dims.size();
+        MB_TRY(mb_cov_i8_build(ctx, lf.kind, sc, x, y, lf.all_dims ? nullptr : lf.dims.data(), d0, out, ldo, &done));
+        if (done) {
+          if (ctx->prof_on)   // algorithmic bytes: K written once, both inputs read once
+            ctx->prof_work[MB_PROF_COV] += 8.0 * ((double)x->rows * y->rows + (double)x->cols * ((double)x->rows + y->rows));
+          return 0;
+        }
+      }
+    }
+  }
   Plan plan;
   MB_TRY(prepare(ctx, prog, x, y, &plan, true));
   bool done = false;

@@ -18,12 +18,13 @@
 //                     A: [128-col panel][k-step of 32 cells][slice 7][k16 chunk 2][128 cols][16 B]   28 KB per (panel, k-step)
 //                     B: [ 64-col panel][k-step           ][slice 7][k16 chunk 2][ 64 cols][16 B]   14 KB per (panel, k-step)
 //                     so one 1-D bulk copy (cp.async.bulk) fills an operand stage
-//   gram_i8_kernel    one CTA per (group, lower 128 x 64 tile): warp 0 = producer (4-stage ring of 42 KB),
-//                     warps 1-4 = MMA issuers (each owns one or two digit-pair groups, 7 MMAs of 128 x 64 x 32 per
-//                     k-step: ONE issuing thread sustains only one MMA per ~144 clk, several issuing warps add up),
-//                     then the same four warps flush (tcgen05.ld lane quadrant = warp % 4).
-// Measured (profiles/gram_i8_r02.txt): 41 ms per 131072 cells at r = 5000 = 72 float64-equivalent TF/s, tensor pipe 54 %,
-// bound by the tensor core's shared-memory operand reads at N = 64 (l1tex tc wavefronts 82 %).
+//   gram_i8_kernel    one CTA per (group, lower 128 x 64 tile): warp 0 = producer (4-stage ring of 42 KB), warps 1..NI
+//                     = MMA issuers: the whole warp runs the loop so that the MMA operands are warp-uniform, one
+//                     elected lane issues; every accumulator group belongs to ONE issuer; then warps 1-4 flush
+//                     (tcgen05.ld lane quadrant = warp % 4).
+// Measured (profiles/bench_kernels_r02.txt, profiles/ncu_*_i8_r02.csv): the N = 64 MMA is bound by the tensor core's
+// shared-memory operand reads (48 clk per 128 x 64 x 32 MMA = 2/3 of the int8 peak), one thread issues an MMA per
+// ~80 clk, so the issuers share the 28 MMAs of a k-step.
 #include "mb_common.cuh"
 
 namespace {
@@ -36,12 +37,9 @@ constexpr int TA = 128, TB = 64;               // output tile: 128 rows (A panel
 constexpr int ASLICE = 2 * TA * 16, ABLOCK = NS * ASLICE;   // 4 KB per slice, 28 KB per (A panel, k-step)
 constexpr int BSLICE = 2 * TB * 16, BBLOCK = NS * BSLICE;   // 2 KB per slice, 14 KB per (B panel, k-step)
 constexpr int NST = 4;                         // operand stages in flight
-constexpr int NISS = 4;                        // MMA-issuing warps
-constexpr int NT = (1 + NISS) * 32;            // producer warp + issuer / flush warps
+constexpr int NT = 5 * 32;                     // producer warp + issuer warp (also flushes) + 3 more flush warps
 constexpr int SMEM_TOTAL = NST * (ABLOCK + BBLOCK);         // 168 KB
 constexpr int KC = 16384;                      // cells per group: |G_g| <= 7 * 2^28 < 2^31
-// digit-pair groups per issuing warp (a group g has g + 1 MMAs per k-step): {6} {0,5} {1,4} {2,3} -> 7 MMAs each
-__device__ const int8_t ISSUER_GROUPS[4][2] = {{-1, 6}, {0, 5}, {1, 4}, {2, 3}};
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -102,20 +100,88 @@ pack_cols_kernel(const double* __restrict__ A, int64_t rows, int64_t r, int64_t 
 // ---- tcgen05 helpers -------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, no swizzle, K-major: 8-row groups 128 B apart (SBO), the two 16-byte K chunks of
 // a K = 32 int8 operand LBO apart
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;                            // descriptor version 1; SWIZZLE_NONE
-  return d;
-}
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+// tcgen05.mma kind::i8 with the shared-memory matrix descriptors given as (low, high) 32-bit halves: the issue loop only
+// adds the slice offset to the low word (start address >> 4) instead of rebuilding 64-bit descriptors.  The scalar code around an MMA is what limits
+// one issuing thread (~144 clk per MMA with make_desc in the loop, an order of magnitude less this way).
+__device__ __forceinline__ void umma_i8_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, p;\n\t}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi),
+      "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+constexpr uint32_t DESC_HI = ((128u >> 4) & 0x3FFFu) | (1u << 14);   // SBO = 128 B, descriptor version 1 (bit 46)
+
+// true on exactly one lane of a converged warp; unlike `lane == 0` the compiler KNOWS a single thread follows, so the
+// MMA operands go to uniform registers directly instead of through a per-instruction waterfall loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar);
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* status, unsigned backoff_ns = 0);
+
+// The 28 MMAs of one k-step, acc_g += A_t B_(g-t)^T for t <= g <= 6, shared among NI issuing warps BY GROUP: every
+// accumulator g belongs to one issuer (MMAs of different threads are not ordered, and the first MMA of a group must
+// come before the others: it overwrites).  One thread issues an MMA every ~80 clk (uniform-datapath set-up of the five
+// operands), the tensor pipe takes 48 clk per 128 x 64 x 32 MMA, so several issuers are needed to keep it busy.
+//   NI = 4: {6} {5,0} {4,1} {3,2} (7 MMAs each);  NI = 2: {6,3,2,0} (15) {5,4,1} (13);  NI = 1: everything
+__host__ __device__ constexpr int group_owner(int ni, int g) {
+  return ni == 1 ? 0 : ni == 2 ? ((g == 6 || g == 3 || g == 2 || g == 0) ? 0 : 1)
+                               : (g == 6 ? 0 : (g == 5 || g == 0) ? 1 : (g == 4 || g == 1) ? 2 : 3);
+}
+template <int NI, int W>
+__device__ __forceinline__ void issue_kstep(uint32_t a_lo, uint32_t b_lo, uint32_t tmem_base, uint32_t idesc, uint32_t fresh) {
+#pragma unroll
+  for (int t = 0; t < NS; t++) {
+#pragma unroll
+    for (int g = NS - 1; g >= t; g--)
+      if (group_owner(NI, g) == W)
+        umma_i8_lh(tmem_base + (uint32_t)(g * TB), a_lo + (uint32_t)(t * (ASLICE >> 4)), DESC_HI,
+                   b_lo + (uint32_t)((g - t) * (BSLICE >> 4)), DESC_HI, idesc, (t == 0) ? fresh : 1u);
+  }
+}
+template <int NI>
+__device__ __forceinline__ void issue_kstep_w(int w, uint32_t a_lo, uint32_t b_lo, uint32_t tmem_base, uint32_t idesc,
+                                              uint32_t fresh) {
+  if (w == 0) issue_kstep<NI, 0>(a_lo, b_lo, tmem_base, idesc, fresh);
+  else if (NI > 1 && w == 1) issue_kstep<NI, 1 % NI>(a_lo, b_lo, tmem_base, idesc, fresh);
+  else if (NI > 2 && w == 2) issue_kstep<NI, 2 % NI>(a_lo, b_lo, tmem_base, idesc, fresh);
+  else if (NI > 3) issue_kstep<NI, 3 % NI>(a_lo, b_lo, tmem_base, idesc, fresh);
+}
+
+// the issuing loop of warp `w` (0-based among the NI issuers): the WHOLE warp runs it so that the MMA operands are
+// warp-uniform (uniform registers, no per-instruction waterfall); one lane polls the barrier, one elected lane issues
+template <int NI>
+__device__ __forceinline__ void issuer_loop(int w, int lane, int64_t nks, unsigned char* smem, uint64_t* full, uint64_t* empty,
+                                            uint64_t* done, uint32_t tmem_base, int* status) {
+  bool ok = true;
+  // instruction descriptor: D = s32, A = B = signed 8 bit, K-major both, N = 64, M = 128
+  const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TB >> 3) << 17) | ((uint32_t)(TA >> 4) << 24);
+  const uint32_t smem0 = s_u32(smem);
+  for (int64_t ks = 0; ks < nks && ok; ks++) {
+    const int s = (int)(ks % NST);
+    if (lane == 0) ok = mbar_wait(&full[s], (uint32_t)((ks / NST) & 1), status);
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (!ok) break;
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t sa = smem0 + (uint32_t)s * (ABLOCK + BBLOCK), sb = sa + ABLOCK;
+    if (elect_one()) {
+      issue_kstep_w<NI>(w, desc_lo(sa, TA * 16), desc_lo(sb, TB * 16), tmem_base, idesc, (ks == 0) ? 0u : 1u);
+      umma_commit(&empty[s]);     // arrives once every MMA of this issuer that reads stage s has completed
+    }
+    __syncwarp();
+  }
+  if (elect_one()) umma_commit(done);
+}
+
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(s_u32(bar)) : "memory");
 }
@@ -126,7 +192,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
 }
 // bounded wait: a protocol bug shows up as an error code instead of a hung GPU
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* status, unsigned backoff_ns = 0) {
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* status, unsigned backoff_ns) {
   uint32_t ok = 0;
   long long spins = 0;
   while (!ok) {
@@ -167,6 +233,7 @@ struct GramArgs {
 };
 
 // out_g[pa*128 .. , pb*64 ..] = (A_g^T A_g) tile for the K-major digit operands of group g
+template <int NI>
 __global__ void __launch_bounds__(NT, 1)
 gram_i8_kernel(const GramArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -179,8 +246,8 @@ gram_i8_kernel(const GramArgs a) {
   const int64_t nks = (g_rows + KS - 1) / KS;
 
   if (tid == 0) {
-    for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NISS); }
-    mbar_init(&done, NISS);
+    for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NI); }
+    mbar_init(&done, NI);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
@@ -207,35 +274,8 @@ gram_i8_kernel(const GramArgs a) {
       }
     }
   } else {
-    // ---- issuers: warp 1 + w owns the digit-pair groups ISSUER_GROUPS[w] (g0 may be absent), accumulators at columns 64 g ----
-    const int w = warp - 1, g0 = ISSUER_GROUPS[w][0], g1 = ISSUER_GROUPS[w][1];
-    if (lane == 0) {
-      bool ok = true;
-      // instruction descriptor: D = s32, A = B = signed 8 bit, K-major both, N = 64, M = 128
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TB >> 3) << 17) | ((uint32_t)(TA >> 4) << 24);
-      const uint32_t acc0 = tmem_base + (uint32_t)((g0 < 0 ? 0 : g0) * TB), acc1 = tmem_base + (uint32_t)(g1 * TB);
-      for (int64_t ks = 0; ks < nks && ok; ks++) {
-        const int s = (int)(ks % NST);
-        ok = mbar_wait(&full[s], (uint32_t)((ks / NST) & 1), a.status);
-        if (!ok) break;
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint32_t sa = s_u32(smem + s * (ABLOCK + BBLOCK)), sb = sa + ABLOCK;
-        const uint32_t fresh = (ks == 0) ? 0u : 1u;
-#pragma unroll
-        for (int t = 0; t < NS; t++) {
-          if (t <= g1) {
-            umma_i8(acc1, make_desc(sa + t * ASLICE, TA * 16, 128), make_desc(sb + (g1 - t) * BSLICE, TB * 16, 128), idesc,
-                    (t == 0) ? fresh : 1u);
-          }
-          if (t <= g0) {
-            umma_i8(acc0, make_desc(sa + t * ASLICE, TA * 16, 128), make_desc(sb + (g0 - t) * BSLICE, TB * 16, 128), idesc,
-                    (t == 0) ? fresh : 1u);
-          }
-        }
-        umma_commit(&empty[s]);     // arrives once every MMA of this issuer that reads stage s has completed
-      }
-      umma_commit(&done);
-    }
+    // ---- issuers: warps 1 .. NI (see issuer_loop); warps 1-4 flush ----
+    if (warp <= NI) issuer_loop<NI>(warp - 1, lane, nks, smem, full, empty, &done, tmem_base, a.status);
     __syncwarp();
     // ---- flush: warps 1-4, TMEM lane quadrant = warp % 4 (row of the tile), 16 columns at a time ----
     if (mbar_wait(&done, 0, a.status, 256)) {
@@ -361,6 +401,7 @@ struct NtArgs {
 };
 
 // one CTA per 128 x 64 output tile; B panel index fastest, so the CTAs in flight share an A panel through L2
+template <int NI>
 __global__ void __launch_bounds__(NT, 1)
 gemm_nt_i8_kernel(const NtArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -372,8 +413,8 @@ gemm_nt_i8_kernel(const NtArgs a) {
   const int64_t nks = a.nks;
 
   if (tid == 0) {
-    for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NISS); }
-    mbar_init(&done, NISS);
+    for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NI); }
+    mbar_init(&done, NI);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
@@ -399,33 +440,7 @@ gemm_nt_i8_kernel(const NtArgs a) {
       }
     }
   } else {
-    const int w = warp - 1, g0 = ISSUER_GROUPS[w][0], g1 = ISSUER_GROUPS[w][1];
-    if (lane == 0) {
-      bool ok = true;
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TB >> 3) << 17) | ((uint32_t)(TA >> 4) << 24);
-      const uint32_t acc0 = tmem_base + (uint32_t)((g0 < 0 ? 0 : g0) * TB), acc1 = tmem_base + (uint32_t)(g1 * TB);
-      for (int64_t ks = 0; ks < nks && ok; ks++) {
-        const int s = (int)(ks % NST);
-        ok = mbar_wait(&full[s], (uint32_t)((ks / NST) & 1), a.status);
-        if (!ok) break;
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint32_t sa = s_u32(smem + s * (ABLOCK + BBLOCK)), sb = sa + ABLOCK;
-        const uint32_t fresh = (ks == 0) ? 0u : 1u;
-#pragma unroll
-        for (int t = 0; t < NS; t++) {
-          if (t <= g1) {
-            umma_i8(acc1, make_desc(sa + t * ASLICE, TA * 16, 128), make_desc(sb + (g1 - t) * BSLICE, TB * 16, 128), idesc,
-                    (t == 0) ? fresh : 1u);
-          }
-          if (t <= g0) {
-            umma_i8(acc0, make_desc(sa + t * ASLICE, TA * 16, 128), make_desc(sb + (g0 - t) * BSLICE, TB * 16, 128), idesc,
-                    (t == 0) ? fresh : 1u);
-          }
-        }
-        umma_commit(&empty[s]);
-      }
-      umma_commit(&done);
-    }
+    if (warp <= NI) issuer_loop<NI>(warp - 1, lane, nks, smem, full, empty, &done, tmem_base, a.status);
     __syncwarp();
     if (mbar_wait(&done, 0, a.status, 256)) {
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -505,7 +520,9 @@ int mb_i8_gram_leaf(mb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int
   }
   static bool configured = false;
   if (!configured) {
-    MB_CUDA(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    MB_CUDA(cudaFuncSetAttribute(gram_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    MB_CUDA(cudaFuncSetAttribute(gram_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    MB_CUDA(cudaFuncSetAttribute(gram_i8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     configured = true;
   }
   // workspace: digits (A and B layouts), scales, column maxima, per-group partial products
@@ -549,7 +566,10 @@ int mb_i8_gram_leaf(mb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int
   ga.out_gstride = (int64_t)r * r;
   ga.status = ctx->i8_status;
   if (ctx->prof_on) ctx->prof_work[MB_PROF_I8] += (double)r * (double)r * (double)rows;  // SYRK: n r^2 flops
-  MB_LAUNCH_P(ctx, MB_PROF_I8, gram_i8_kernel, (unsigned)(ng * ctx->i8_ntiles), NT, SMEM_TOTAL, ga);
+  const unsigned ggrid = (unsigned)(ng * ctx->i8_ntiles);
+  if (ctx->opt_i8_issuers == 1) MB_LAUNCH_P(ctx, MB_PROF_I8, gram_i8_kernel<1>, ggrid, NT, SMEM_TOTAL, ga);
+  else if (ctx->opt_i8_issuers == 2) MB_LAUNCH_P(ctx, MB_PROF_I8, gram_i8_kernel<2>, ggrid, NT, SMEM_TOTAL, ga);
+  else MB_LAUNCH_P(ctx, MB_PROF_I8, gram_i8_kernel<4>, ggrid, NT, SMEM_TOTAL, ga);
   if (ng > 1) {
     const int64_t n = (int64_t)r * r;
     MB_LAUNCH(ctx, sum_groups_kernel, (int)std::min<int64_t>(ceil_div64(n, 256), (int64_t)ctx->n_sm * 16), 256, 0, parts, ng,
@@ -578,7 +598,9 @@ int mb_i8_gemm_nt(mb_ctx* ctx, int64_t n, int64_t p, int64_t k, double alpha, co
   }
   static bool configured = false;
   if (!configured) {
-    MB_CUDA(cudaFuncSetAttribute(gemm_nt_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    MB_CUDA(cudaFuncSetAttribute(gemm_nt_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    MB_CUDA(cudaFuncSetAttribute(gemm_nt_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    MB_CUDA(cudaFuncSetAttribute(gemm_nt_i8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     configured = true;
   }
   const int64_t SLAB = 65536;
@@ -621,7 +643,10 @@ int mb_i8_gemm_nt(mb_ctx* ctx, int64_t n, int64_t p, int64_t k, double alpha, co
     na.ldc = ldc;
     na.status = ctx->i8_status;
     if (ctx->prof_on) ctx->prof_work[MB_PROF_I8] += 2.0 * (double)rows * (double)p * (double)k;
-    MB_LAUNCH_P(ctx, MB_PROF_I8, gemm_nt_i8_kernel, (unsigned)(npa * npb), NT, SMEM_TOTAL, na);
+    const unsigned ngrid = (unsigned)(npa * npb);
+    if (ctx->opt_i8_issuers == 1) MB_LAUNCH_P(ctx, MB_PROF_I8, gemm_nt_i8_kernel<1>, ngrid, NT, SMEM_TOTAL, na);
+    else if (ctx->opt_i8_issuers == 2) MB_LAUNCH_P(ctx, MB_PROF_I8, gemm_nt_i8_kernel<2>, ngrid, NT, SMEM_TOTAL, na);
+    else MB_LAUNCH_P(ctx, MB_PROF_I8, gemm_nt_i8_kernel<4>, ngrid, NT, SMEM_TOTAL, na);
   }
   return 0;
 }

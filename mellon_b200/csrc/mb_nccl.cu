@@ -108,6 +108,12 @@ extern "C" int mb_comm_destroy(mb_ctx* ctx) {
   return 0;
 }
 
+extern "C" int mb_comm_solo(mb_ctx* ctx, int on) {
+  MB_CHECK(ctx, "mb_comm_solo: null ctx");
+  ctx->solo = on != 0;
+  return 0;
+}
+
 extern "C" int mb_comm_info(mb_ctx* ctx, int* rank, int* world) {
   MB_CHECK(ctx, "mb_comm_info: null ctx");
   if (rank) *rank = ctx->rank;
@@ -116,7 +122,7 @@ extern "C" int mb_comm_info(mb_ctx* ctx, int* rank, int* world) {
 }
 
 int mb_allreduce_raw(mb_ctx* ctx, double* p, int64_t count) {
-  if (!ctx->comm || ctx->world == 1 || count == 0) return 0;
+  if (!ctx->comm || ctx->world == 1 || ctx->solo || count == 0) return 0;
   MB_NCCL(g_nccl.AllReduce(p, p, (size_t)count, ncclFloat64, ncclSum, reinterpret_cast<ncclComm_t>(ctx->comm),
                            ctx->stream));
   return 0;

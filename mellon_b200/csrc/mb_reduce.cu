@@ -34,7 +34,7 @@ int mb_chunk_grid(mb_ctx* ctx, const mb_mat* m, mb_chunks* out) {
   out->cr = std::max<int64_t>(1, ceil_div64(out->G, MB_NCHUNK));
   out->row_lo = marked ? m->row_lo : 0;
   out->rows = m->rows;
-  out->sharded = marked && ctx->comm != nullptr && ctx->world > 1;
+  out->sharded = marked && ctx->comm != nullptr && ctx->world > 1 && !ctx->solo;
   const int64_t end = out->row_lo + m->rows;
   if (out->sharded) {
     // the canonical layout: every rank can derive every other rank's leaves from (G, world)

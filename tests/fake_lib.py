@@ -217,6 +217,14 @@ class FakeLib:
         count._obj.value, ms._obj.value, work._obj.value = 0, 0.0, 0.0
         return 0
 
+    def mb_comm_solo(self, ctx, on):
+        if on:
+            self._saved_world = (self.rank, self.world)
+            self.rank, self.world = 0, 1
+        else:
+            self.rank, self.world = getattr(self, "_saved_world", (self.rank, self.world))
+        return 0
+
     def mb_comm_info(self, ctx, rank, world):
         rank._obj.value, world._obj.value = self.rank, self.world
         return 0

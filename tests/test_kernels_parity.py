@@ -565,3 +565,46 @@ def test_int8_slices_forced_on_small_and_ragged_shapes(be, n, r):
         assert rel_err(be.gemm(Ld, be.upload(B)).numpy(), L @ B) < 1e-13
     finally:
         be.set_option("i8", 1)
+
+
+@pytest.mark.parametrize("kc,ko", [(C.Matern52, O.Matern52), (C.Matern32, O.Matern32), (C.ExpQuad, O.ExpQuad),
+                                   (C.Exponential, O.Exponential)])
+@pytest.mark.parametrize("n,m,d", [(300, 70, 10), (129, 65, 64), (1000, 257, 33), (5000, 300, 50), (64, 64, 1)])
+def test_k1_on_int8_digit_slices(be, kc, ko, n, m, d):
+    """K1 with its contraction on the tcgen05 int8 digit slices (csrc/mb_cov_i8.cu), forced at small and ragged shapes
+    (option cov_i8 = 2): partial cell panels, partial landmark tiles, one and two k-steps, all four kernels; the same
+    2e-13 bar as the FP64 kernels, on unit-scale data where the length scale does not hide the contraction."""
+    if be.name != "cuda":
+        pytest.skip("the int8 digit-slice path exists in the CUDA library only")
+    rng = np.random.default_rng(n + m + d)
+    x, y = rng.standard_normal((n, d)), rng.standard_normal((m, d))
+    if kc is not C.Exponential:
+        # coincident points: d = sqrt(1e-12).  Not for the Exponential kernel: exp(-d / (2 ls)) is not smooth at d = 0,
+        # so there the rounding of xx - 2xy + yy (1e-16 of |x|^2, in ANY float64 implementation, the reference's
+        # included) shows up as 1e-9 in k, whatever computes it
+        y[: min(m, 5)] = x[: min(m, 5)]
+    be.set_option("cov_i8", 2)
+    try:
+        for ls in (1.3, 25.0):
+            K = be.cov(kc(ls), x, y).numpy()
+            assert np.max(np.abs(K - ko(ls)(x, y))) < 2e-13
+        sel = [0] if d == 1 else list(range(0, d, 2))
+        K = be.cov(kc(2.0, active_dims=sel), x, y).numpy()
+        assert np.max(np.abs(K - ko(2.0, active_dims=sel)(x, y))) < 2e-13
+    finally:
+        be.set_option("cov_i8", 1)
+
+
+def test_k1_int8_large_shape_matches_the_dmma_kernel(be):
+    if be.name != "cuda":
+        pytest.skip("the int8 digit-slice path exists in the CUDA library only")
+    rng = np.random.default_rng(11)
+    x, y = rng.random((20011, 50)), rng.random((1003, 50))
+    K8 = be.cov(C.Matern52(38.0), x, y).numpy()
+    be.set_option("cov_i8", 0)
+    try:
+        K64 = be.cov(C.Matern52(38.0), x, y).numpy()
+    finally:
+        be.set_option("cov_i8", 1)
+    assert np.max(np.abs(K8 - K64)) < 2e-13
+    assert np.max(np.abs(K8 - O.Matern52(38.0)(x, y))) < 2e-13

@@ -49,6 +49,7 @@ for rep in range(2):
     est.process_inference(build_predict=False); mark("log_density = Lz+mu")
     del est
     mark("free")
-    print(f"--- rep {rep}: total {1e3 * (t[-1] - t[0]):.1f} ms")
-    for nm, a, b in zip(names, t[:-1], t[1:]):
-        print(f"  {nm:28s} {1e3 * (b - a):9.1f} ms")
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"--- rep {rep}: total {1e3 * (t[-1] - t[0]):.1f} ms (world {os.environ.get('WORLD_SIZE', '1')})")
+        for nm, a, b in zip(names, t[:-1], t[1:]):
+            print(f"  {nm:28s} {1e3 * (b - a):9.1f} ms")
