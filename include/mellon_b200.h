@@ -117,10 +117,13 @@ int mb_flush_l2(mb_ctx* ctx);
  *   "gemm"     1 = DFMA reference GEMM, 2 = 8-warp DMMA tiles, 3 = no split-k, 4 = generic operand loaders
  *   "trsm"     1 = 32-wide substitution leaves for TRSM / Cholesky (no inverted 128-blocks, no blocked TRSV)
  *   "lossgrad" 1 = two-pass objective, 2 = register-fused single pass (0 = bulk-TMA ring)
+ *   "cov_i8"   0 = K1 always on the FP64 DMMA kernel; 1 (default) = one exponential-family leaf with D <= 64, >= 4096
+ *              cells and >= 256 landmarks on the tcgen05 kind::i8 digit-slice kernel; 2 = at every size (tests)
+ *   "i8_issuers" MMA-issuing warps of the int8 GEMM kernels: 1, 2 or 4 (default 4)
  *   "graph"    0 = launch the Cholesky on the stream instead of replaying its CUDA graph
  *   "i8"       0 = every FP64 product on the DMMA tiles; 1 (default) = the large products on tcgen05 kind::i8 digit
  *              slices: Gram matrices with chunks >= 2048 cells and r >= 512, TRSM updates / tall GEMMs with >= 8192
- *              cells, k >= 512 and >= 256 output columns; 2 = int8 slices at every size (tests, sanitizer runs) */
+ *              cells, k >= 256 and >= 128 output columns; 2 = int8 slices at every size (tests, sanitizer runs) */
 int mb_set_option(mb_ctx* ctx, const char* key, int value);
 
 /* pinned (page-locked) host buffers, so uploads / the streaming predictor overlap with compute */

@@ -191,6 +191,7 @@ struct CovI8Args {
   double eps_scaled;      // 1e-12 c^2 (util.py:365: + 1e-12 inside the square root)
   double* out;
   int64_t ldo;
+  int vec;                // out is 16-byte aligned and ldo even: 16-byte stores
   int* status;
 };
 
@@ -301,7 +302,6 @@ cov_i8_kernel(const CovI8Args a) {
     const int ew = warp - 4, quad = warp & 3, cb = ew >> 2;        // TMEM lane quadrant = warp % 4; 16 columns
     const int row = quad * 32 + lane, c0 = cb * EC;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
-    double* strip = reinterpret_cast<double*>(smem + xbytes + (size_t)NYB * ybytes) + (size_t)ew * (32 * 9);
     int64_t it = 0;
     bool ok = true;
     for (int64_t panel = blockIdx.x; panel < n_panels && ok; panel += gridDim.x) {
@@ -335,26 +335,29 @@ cov_i8_kernel(const CovI8Args a) {
         // column constants of this tile (shared memory, broadcast reads), then the covariance
         const double* cst = reinterpret_cast<const double*>(ys + (size_t)s * ybytes + (size_t)a.ksteps * YKSTEP);
         ok = ok && mbar_wait(&y_full[s], (uint32_t)((it / NYB) & 1), a.status);   // visibility of the constants
-        // 8 columns at a time: evaluate, transpose through the warp's shared-memory strip, and store 64-byte row
-        // segments (a thread owns a ROW of the tile; storing from that layout would touch 32 different lines per
-        // instruction and bind the kernel on the LSU)
+        // 8 columns at a time: evaluate and store (a thread owns 16 consecutive columns of ONE row: 128 bytes)
+        double* orow = a.out + gi * a.ldo + jt * TN + c0;
 #pragma unroll
         for (int h = 0; h < EC; h += 8) {
+          double val[8];
 #pragma unroll
           for (int e = 0; e < 8; e++) {
             const double yn = cst[c0 + h + e], sy = cst[TN + c0 + h + e];
             const double sq = fma(H[h + e] * sx, sy, xn + yn);            // xn + yn - 2 x.y (+ eps)
-            strip[lane * 9 + e] = eval_scaled<KIND>(sq, tab);
+            val[e] = eval_scaled<KIND>(sq, tab);
           }
-          __syncwarp();
-          const int64_t gj = jt * TN + c0 + h + (lane & 7);
+          if (gi < a.n) {
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const int r = 4 * i + (lane >> 3);
-            const int64_t grow = panel * TM + quad * 32 + r;
-            if (grow < a.n && gj < a.m) a.out[grow * a.ldo + gj] = strip[r * 9 + (lane & 7)];
+            for (int e = 0; e < 8; e += 2) {
+              const int64_t gj = jt * TN + c0 + h + e;
+              if (gj + 1 < a.m && a.vec) {
+                *reinterpret_cast<double2*>(orow + h + e) = make_double2(val[e], val[e + 1]);
+              } else {
+                if (gj < a.m) orow[h + e] = val[e];
+                if (gj + 1 < a.m) orow[h + e + 1] = val[e + 1];
+              }
+            }
           }
-          __syncwarp();
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&y_empty[s]);          // done with the stage's constants
@@ -429,8 +432,9 @@ int mb_cov_i8_build(mb_ctx* ctx, int kind, double c, const mb_mat* x, const mb_m
   a.eps_scaled = 1e-12 * c * c;
   a.out = out;
   a.ldo = ldo;
+  a.vec = ((ldo & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
   a.status = ctx->i8_status;
-  const size_t smem = (size_t)xbytes + (size_t)NYB * ybytes + (size_t)NEPI * 32 * 9 * sizeof(double);
+  const size_t smem = (size_t)xbytes + (size_t)NYB * ybytes;
   switch (kind) {
     case MB_K_MATERN32: MB_TRY(launch_cov_i8<MB_K_MATERN32>(ctx, a, smem)); break;
     case MB_K_MATERN52: MB_TRY(launch_cov_i8<MB_K_MATERN52>(ctx, a, smem)); break;

@@ -581,7 +581,7 @@ int mb_i8_gram_leaf(mb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int
 
 bool mb_i8_nt_usable(mb_ctx* ctx, int64_t rows_total, int64_t p, int64_t k) {
   if (ctx->opt_i8 == 2) return k >= 1 && k <= KC;
-  return ctx->opt_i8 != 0 && rows_total >= 8192 && p >= 256 && k >= 512 && k <= KC;
+  return ctx->opt_i8 != 0 && rows_total >= 8192 && p >= 128 && k >= 256 && k <= KC;
 }
 
 // C (n x p, ldc) = beta C + alpha A B^T ; A: n x k (lda), B: p x k (ldb), row-major.  beta is 0 or 1.

@@ -16,6 +16,12 @@ METRICS = [
     ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64_pipe_pct_active"),
     ("sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active", "dmma_pipe_pct_active"),
     ("sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_elapsed", "fp64_shared_pipe_pct_elapsed"),
+    ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor_pipe_pct_elapsed"),
+    ("sm__inst_executed_pipe_tensor_subpipe_imma.avg.pct_of_peak_sustained_active", "imma_inst_pct"),
+    ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "tensor_core_smem_reads_pct"),
+    ("l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum", "tma_load_bytes"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_pct"),
+    ("smsp__inst_executed.sum", "warp_instructions"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"),
     ("launch__registers_per_thread", "regs"),
@@ -33,7 +39,10 @@ def main(path):
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
-    idx = {h: i for i, h in enumerate(hdr)}
+    idx = {}
+    for i, h in enumerate(hdr):          # some metrics appear twice (a triage copy with a section prefix): keep the plain name
+        idx.setdefault(h.split(".", 2)[-1] if h.startswith(("TPC.", "SM_A.", "LTS.")) else h, i)
+        idx[h] = i
     out = csv.writer(sys.stdout)
     out.writerow(["kernel"] + [f"{short} [{units[idx[m]]}]" if m in idx and units[idx[m]] else short for m, short in METRICS])
     for r in rows[2:]:
