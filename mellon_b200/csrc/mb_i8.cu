@@ -36,7 +36,7 @@ constexpr int KS = 32;                         // cells per k-step (one kind::i8
 constexpr int TA = 128, TB = 64;               // output tile: 128 rows (A panel) x 64 columns (B panel)
 constexpr int ASLICE = 2 * TA * 16, ABLOCK = NS * ASLICE;   // 4 KB per slice, 28 KB per (A panel, k-step)
 constexpr int BSLICE = 2 * TB * 16, BBLOCK = NS * BSLICE;   // 2 KB per slice, 14 KB per (B panel, k-step)
-constexpr int NST = 4;                         // operand stages in flight
+constexpr int NST = 4;                         // operand stages in flight (a fifth one changes nothing: profiles/bench_kernels_r02.txt)
 constexpr int NT = 5 * 32;                     // producer warp + issuer warp (also flushes) + 3 more flush warps
 constexpr int SMEM_TOTAL = NST * (ABLOCK + BBLOCK);         // 168 KB
 constexpr int KC = 16384;                      // cells per group: |G_g| <= 7 * 2^28 < 2^31
@@ -112,6 +112,25 @@ __device__ __forceinline__ void umma_i8_lh(uint32_t tmem_d, uint32_t a_lo, uint3
       "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from TENSOR MEMORY (128 lanes x 8 columns of 32 bit = one 128 x 32 int8 slice), B from shared memory: the
+// MMA then reads 2 KB of shared memory instead of 6 KB and becomes MAC-bound (32 clk) instead of operand-read-bound (48)
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
+// shared memory (matrix descriptor, same canonical layout as an MMA operand) -> tensor memory, 128 lanes x 256 bit;
+// executes in issue order with the MMAs of the same thread
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t tmem_dst, uint32_t s_lo, uint32_t s_hi) {
+  asm volatile("{\n\t.reg .b64 ds;\n\tmov.b64 ds, {%1, %2};\n\ttcgen05.cp.cta_group::1.128x256b [%0], ds;\n\t}\n" ::"r"(tmem_dst),
+               "r"(s_lo), "r"(s_hi)
+               : "memory");
+}
+
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
   return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
 }
@@ -148,13 +167,30 @@ __device__ __forceinline__ void issue_kstep(uint32_t a_lo, uint32_t b_lo, uint32
                    b_lo + (uint32_t)((g - t) * (BSLICE >> 4)), DESC_HI, idesc, (t == 0) ? fresh : 1u);
   }
 }
+// NI = 0: ONE issuer with the A slices staged in tensor memory (columns 448 .. 503, behind the 7 accumulators): 7 copies
+// shared -> tensor memory, then the 28 MMAs with A from there.  Copies and MMAs of one thread execute in issue order, so
+// the next k-step's copies cannot overtake the MMAs that still read the slices.
+constexpr uint32_t A_TMEM_COL = NS * TB;       // 448
+__device__ __forceinline__ void issue_kstep_atmem(uint32_t a_lo, uint32_t b_lo, uint32_t tmem_base, uint32_t idesc, uint32_t fresh) {
+#pragma unroll
+  for (int t = 0; t < NS; t++) tmem_cp_128x256b(tmem_base + A_TMEM_COL + (uint32_t)(8 * t), a_lo + (uint32_t)(t * (ASLICE >> 4)), DESC_HI);
+#pragma unroll
+  for (int t = 0; t < NS; t++) {
+#pragma unroll
+    for (int g = NS - 1; g >= t; g--)
+      umma_i8_ts(tmem_base + (uint32_t)(g * TB), tmem_base + A_TMEM_COL + (uint32_t)(8 * t),
+                 b_lo + (uint32_t)((g - t) * (BSLICE >> 4)), DESC_HI, idesc, (t == 0) ? fresh : 1u);
+  }
+}
+
 template <int NI>
 __device__ __forceinline__ void issue_kstep_w(int w, uint32_t a_lo, uint32_t b_lo, uint32_t tmem_base, uint32_t idesc,
                                               uint32_t fresh) {
-  if (w == 0) issue_kstep<NI, 0>(a_lo, b_lo, tmem_base, idesc, fresh);
-  else if (NI > 1 && w == 1) issue_kstep<NI, 1 % NI>(a_lo, b_lo, tmem_base, idesc, fresh);
-  else if (NI > 2 && w == 2) issue_kstep<NI, 2 % NI>(a_lo, b_lo, tmem_base, idesc, fresh);
-  else if (NI > 3) issue_kstep<NI, 3 % NI>(a_lo, b_lo, tmem_base, idesc, fresh);
+  if (NI == 0) { issue_kstep_atmem(a_lo, b_lo, tmem_base, idesc, fresh); return; }
+  if (w == 0) issue_kstep<NI == 0 ? 1 : NI, 0>(a_lo, b_lo, tmem_base, idesc, fresh);
+  else if (NI > 1 && w == 1) issue_kstep<NI == 0 ? 1 : NI, 1 % (NI == 0 ? 1 : NI)>(a_lo, b_lo, tmem_base, idesc, fresh);
+  else if (NI > 2 && w == 2) issue_kstep<NI == 0 ? 1 : NI, 2 % (NI == 0 ? 1 : NI)>(a_lo, b_lo, tmem_base, idesc, fresh);
+  else if (NI > 3) issue_kstep<NI == 0 ? 1 : NI, 3 % (NI == 0 ? 1 : NI)>(a_lo, b_lo, tmem_base, idesc, fresh);
 }
 
 // the issuing loop of warp `w` (0-based among the NI issuers): the WHOLE warp runs it so that the MMA operands are
@@ -246,8 +282,8 @@ gram_i8_kernel(const GramArgs a) {
   const int64_t nks = (g_rows + KS - 1) / KS;
 
   if (tid == 0) {
-    for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NI); }
-    mbar_init(&done, NI);
+    for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NI == 0 ? 1 : NI); }
+    mbar_init(&done, NI == 0 ? 1 : NI);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
@@ -275,7 +311,7 @@ gram_i8_kernel(const GramArgs a) {
     }
   } else {
     // ---- issuers: warps 1 .. NI (see issuer_loop); warps 1-4 flush ----
-    if (warp <= NI) issuer_loop<NI>(warp - 1, lane, nks, smem, full, empty, &done, tmem_base, a.status);
+    if (warp <= (NI == 0 ? 1 : NI)) issuer_loop<NI>(warp - 1, lane, nks, smem, full, empty, &done, tmem_base, a.status);
     __syncwarp();
     // ---- flush: warps 1-4, TMEM lane quadrant = warp % 4 (row of the tile), 16 columns at a time ----
     if (mbar_wait(&done, 0, a.status, 256)) {
@@ -413,8 +449,8 @@ gemm_nt_i8_kernel(const NtArgs a) {
   const int64_t nks = a.nks;
 
   if (tid == 0) {
-    for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NI); }
-    mbar_init(&done, NI);
+    for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NI == 0 ? 1 : NI); }
+    mbar_init(&done, NI == 0 ? 1 : NI);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
@@ -440,7 +476,7 @@ gemm_nt_i8_kernel(const NtArgs a) {
       }
     }
   } else {
-    if (warp <= NI) issuer_loop<NI>(warp - 1, lane, nks, smem, full, empty, &done, tmem_base, a.status);
+    if (warp <= (NI == 0 ? 1 : NI)) issuer_loop<NI>(warp - 1, lane, nks, smem, full, empty, &done, tmem_base, a.status);
     __syncwarp();
     if (mbar_wait(&done, 0, a.status, 256)) {
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -520,6 +556,7 @@ int mb_i8_gram_leaf(mb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int
   }
   static bool configured = false;
   if (!configured) {
+    MB_CUDA(cudaFuncSetAttribute(gram_i8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     MB_CUDA(cudaFuncSetAttribute(gram_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     MB_CUDA(cudaFuncSetAttribute(gram_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     MB_CUDA(cudaFuncSetAttribute(gram_i8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
@@ -567,7 +604,8 @@ int mb_i8_gram_leaf(mb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int
   ga.status = ctx->i8_status;
   if (ctx->prof_on) ctx->prof_work[MB_PROF_I8] += (double)r * (double)r * (double)rows;  // SYRK: n r^2 flops
   const unsigned ggrid = (unsigned)(ng * ctx->i8_ntiles);
-  if (ctx->opt_i8_issuers == 1) MB_LAUNCH_P(ctx, MB_PROF_I8, gram_i8_kernel<1>, ggrid, NT, SMEM_TOTAL, ga);
+  if (ctx->opt_i8_issuers == 0) MB_LAUNCH_P(ctx, MB_PROF_I8, gram_i8_kernel<0>, ggrid, NT, SMEM_TOTAL, ga);
+  else if (ctx->opt_i8_issuers == 1) MB_LAUNCH_P(ctx, MB_PROF_I8, gram_i8_kernel<1>, ggrid, NT, SMEM_TOTAL, ga);
   else if (ctx->opt_i8_issuers == 2) MB_LAUNCH_P(ctx, MB_PROF_I8, gram_i8_kernel<2>, ggrid, NT, SMEM_TOTAL, ga);
   else MB_LAUNCH_P(ctx, MB_PROF_I8, gram_i8_kernel<4>, ggrid, NT, SMEM_TOTAL, ga);
   if (ng > 1) {
@@ -598,6 +636,7 @@ int mb_i8_gemm_nt(mb_ctx* ctx, int64_t n, int64_t p, int64_t k, double alpha, co
   }
   static bool configured = false;
   if (!configured) {
+    MB_CUDA(cudaFuncSetAttribute(gemm_nt_i8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     MB_CUDA(cudaFuncSetAttribute(gemm_nt_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     MB_CUDA(cudaFuncSetAttribute(gemm_nt_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     MB_CUDA(cudaFuncSetAttribute(gemm_nt_i8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
@@ -644,7 +683,8 @@ int mb_i8_gemm_nt(mb_ctx* ctx, int64_t n, int64_t p, int64_t k, double alpha, co
     na.status = ctx->i8_status;
     if (ctx->prof_on) ctx->prof_work[MB_PROF_I8] += 2.0 * (double)rows * (double)p * (double)k;
     const unsigned ngrid = (unsigned)(npa * npb);
-    if (ctx->opt_i8_issuers == 1) MB_LAUNCH_P(ctx, MB_PROF_I8, gemm_nt_i8_kernel<1>, ngrid, NT, SMEM_TOTAL, na);
+    if (ctx->opt_i8_issuers == 0) MB_LAUNCH_P(ctx, MB_PROF_I8, gemm_nt_i8_kernel<0>, ngrid, NT, SMEM_TOTAL, na);
+    else if (ctx->opt_i8_issuers == 1) MB_LAUNCH_P(ctx, MB_PROF_I8, gemm_nt_i8_kernel<1>, ngrid, NT, SMEM_TOTAL, na);
     else if (ctx->opt_i8_issuers == 2) MB_LAUNCH_P(ctx, MB_PROF_I8, gemm_nt_i8_kernel<2>, ngrid, NT, SMEM_TOTAL, na);
     else MB_LAUNCH_P(ctx, MB_PROF_I8, gemm_nt_i8_kernel<4>, ngrid, NT, SMEM_TOTAL, na);
   }

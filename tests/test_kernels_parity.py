@@ -608,3 +608,29 @@ def test_k1_int8_large_shape_matches_the_dmma_kernel(be):
         be.set_option("cov_i8", 1)
     assert np.max(np.abs(K8 - K64)) < 2e-13
     assert np.max(np.abs(K8 - O.Matern52(38.0)(x, y))) < 2e-13
+
+
+def test_int8_gemm_issue_variants_give_identical_bits(be):
+    """The int8 digit-slice GEMMs with 1, 2 or 4 MMA-issuing warps and with the A operand staged in tensor memory
+    (option i8_issuers = 0): the integer accumulation is exact, so every variant must return the same bits."""
+    if be.name != "cuda":
+        pytest.skip("the int8 digit-slice path exists in the CUDA library only")
+    rng = np.random.default_rng(3)
+    L = rng.standard_normal((66000, 640)) * 10.0 ** rng.uniform(-3, 1, size=(1, 640))
+    Lp = np.linalg.cholesky(_spd(640, 640, 1e4))
+    Ld, Lpd = be.upload(L, sharded=True), be.upload(Lp)
+    ref_g = ref_t = None
+    try:
+        for iss in (4, 2, 1, 0):
+            be.set_option("i8_issuers", iss)
+            G = be.gram(Ld).numpy()
+            T = be.trsm_right_lt(Lpd, be.copy(Ld)).numpy()
+            if ref_g is None:
+                ref_g, ref_t = G, T
+                assert rel_err(G, L.T @ L) < 1e-13
+                assert rel_err(T, solve_triangular(Lp, L.T, lower=True).T) < 1e-11
+            else:
+                assert np.array_equal(G, ref_g), f"Gram differs with i8_issuers={iss}"
+                assert np.array_equal(T, ref_t), f"TRSM differs with i8_issuers={iss}"
+    finally:
+        be.set_option("i8_issuers", 4)

@@ -49,7 +49,7 @@ be.set_option("cov_i8", 1)
 
 K = be.cov(cov, xd, xud, sharded=True)
 Lp, info = be.cov_chol(cov, xu, 1e-6)
-for name, opt, iss in (("int8 slices, 4 issuers", 1, 4), ("int8 slices, 2 issuers", 1, 2), ("int8 slices, 1 issuer", 1, 1),
+for name, opt, iss in (("int8 slices, A in TMEM", 1, 0), ("int8 slices, 4 issuers", 1, 4), ("int8 slices, 2 issuers", 1, 2), ("int8 slices, 1 issuer", 1, 1),
                        ("FP64 DMMA", 0, 4)):
     be.set_option("i8", opt)
     be.set_option("i8_issuers", iss)
