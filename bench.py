@@ -2,12 +2,16 @@
 """Headline benchmark: cells/s of ``DensityEstimator.fit_predict`` (the sparse-GP density hot path)
 on synthetic cells, plus the HBM roofline of the fused N x M covariance build (K1).
 
+    python bench.py --config {2,3,4,5} ...                   # BASELINE.json's other configurations
+
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
 
 Under ``python -m torch.distributed.run --nproc-per-node N`` one rank drives one GPU; the cell
 axis is sharded in contiguous row blocks (strong scaling: the total number of cells is fixed) and
-the library all-reduces the Gram matrix and the (loss, gradient) vector over NCCL.
+the library sums the Gram matrix and the (loss, gradient) vector over the cells of all ranks through
+a fixed reduction tree (NCCL): the result has the same bits for every N, which every multi-GPU line
+checks against a one-GPU refit (``parity.vs_one_gpu``).
 
 A "step" is one complete pass of the hot path over the synthetic cell matrix:
 ``Lp = chol(K_MM + jitter I)`` -> ``L = K_NM Lp^-T`` -> Ridge start (Gram + all-reduce) ->
@@ -562,7 +566,8 @@ def run_b200(args):
     except (OSError, ValueError, KeyError):
         pass
     roofline = {
-        "kernel": "cov_mma_kernel (K1: fused pairwise distance + covariance, K_NM build; FP64-issue bound, see DESIGN.md)",
+        "kernel": "cov_i8_kernel (K1: fused pairwise distance + covariance, K_NM build; contraction on tcgen05 kind::i8 digit "
+                  "slices, FP64 epilogue; instruction-issue bound, see DESIGN.md section 4)",
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
         "frac": achieved / hbm_peak if hbm_peak else None, "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": peak_src, "launches": n_cov, "avg_launch_ms": ms_cov / max(n_cov, 1),

@@ -84,6 +84,8 @@ typedef struct mb_kprog {
 /* ---- context / errors ---------------------------------------------------------------- */
 const char* mb_last_error(void);
 int mb_version(void);
+/* first 16 hex digits of the sha256 over csrc/ and this header the library was compiled from */
+const char* mb_source_hash(void);
 int mb_device_count(int* n);
 int mb_ctx_create(int device, mb_ctx** out);
 int mb_ctx_destroy(mb_ctx* ctx);

@@ -62,6 +62,7 @@ _pprog = C.POINTER(KProg)
 SIGNATURES = {
     "mb_last_error": (C.c_char_p, []),
     "mb_version": (_i, []),
+    "mb_source_hash": (C.c_char_p, []),
     "mb_device_count": (_i, [C.POINTER(_i)]),
     "mb_ctx_create": (_i, [_i, C.POINTER(_vp)]),
     "mb_ctx_destroy": (_i, [_vp]),
@@ -129,6 +130,25 @@ SIGNATURES = {
 
 _lib = None
 _lock = threading.Lock()
+
+# translation units of libmellon_b200.so, in the order csrc/Makefile (SRCS) and __graft_entry__.build() hash them
+SOURCES = ["mb_api.cu", "mb_gemm.cu", "mb_chol.cu", "mb_infer.cu", "mb_cov.cu", "mb_solve.cu", "mb_nccl.cu",
+           "mb_reduce.cu", "mb_i8.cu", "mb_kmeans.cu", "mb_cov_i8.cu"]
+
+
+def source_hash() -> str:
+    """First 16 hex digits of the sha256 over the library's sources (SOURCES, the two shared headers, the ABI
+    header) — what ``mb_source_hash()`` of a library built from this tree returns."""
+    import hashlib
+
+    root = os.path.dirname(os.path.abspath(__file__))
+    files = [os.path.join(root, "csrc", f) for f in SOURCES + ["mb_common.cuh", "mb_math.cuh"]]
+    files.append(os.path.join(os.path.dirname(root), "include", "mellon_b200.h"))
+    h = hashlib.sha256()
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 def load_library(path: str | None = None):

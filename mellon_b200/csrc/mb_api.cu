@@ -14,7 +14,14 @@ void mb_set_error(const char* fmt, ...) {
 
 extern "C" const char* mb_last_error(void) { return g_err; }
 static int prof_resolve(mb_ctx* c);
-extern "C" int mb_version(void) { return 100; }
+extern "C" int mb_version(void) { return 200; }
+
+#ifndef MB_SOURCE_HASH
+#define MB_SOURCE_HASH "unknown"
+#endif
+// sha256 (first 16 hex digits) of the sources this library was compiled from: __graft_entry__.build() and
+// tests/test_abi.py compare it with the tree, so a stale prebuilt library cannot pass for the current code
+extern "C" const char* mb_source_hash(void) { return MB_SOURCE_HASH; }
 
 extern "C" int mb_device_count(int* n) {
   MB_CHECK(n != nullptr, "mb_device_count: null output");

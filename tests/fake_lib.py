@@ -164,6 +164,9 @@ class FakeLib:
     def mb_last_error(self):
         return self.err
 
+    def mb_source_hash(self):
+        return b"test-double"
+
     def mb_version(self):
         return 100
 

@@ -69,3 +69,17 @@ def test_product_package_never_imports_the_oracle():
         if name.endswith(".py"):
             src = open(os.path.join(pkg, name)).read()
             assert "oracle" not in re.sub(r"#.*", "", src).replace("an oracle", ""), name
+
+
+def test_library_is_built_from_the_sources_in_the_tree():
+    """The prebuilt library reports the hash of the sources it was compiled from; it must be this tree's (a stale
+    .so travelling with the snapshot would otherwise pass for the current code), and csrc/Makefile must list the same
+    translation units in the same order as _native.SOURCES (both hash them)."""
+    import re
+
+    from mellon_b200 import _native as nat
+
+    lib = nat.load_library()
+    assert lib.mb_source_hash().decode() == nat.source_hash()
+    mk = open(os.path.join(os.path.dirname(nat.__file__), "csrc", "Makefile")).read()
+    assert re.search(r"^SRCS := (.*)$", mk, re.M).group(1).split() == nat.SOURCES
