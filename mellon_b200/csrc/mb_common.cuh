@@ -59,7 +59,7 @@ int mb_i8_gram_leaf(mb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int
 int mb_i8_check(mb_ctx* ctx);
 // K1 on int8 digit slices (mb_cov_i8.cu); *done = false: shape / kind outside that kernel
 int mb_cov_i8_build(mb_ctx* ctx, int kind, double c, const mb_mat* x, const mb_mat* y, const int* dims_host, int d,
-                    double* out, int64_t ldo, bool* done);
+                    double* out, int64_t ldo, bool* done, int64_t self_offset = 0, int64_t* nn_idx = nullptr);
 // C = beta C + alpha A B^T on int8 digit slices (A: n x k, B: p x k row-major; beta 0 or 1); rows_total: the GLOBAL
 // number of rows of the row-sharded operand (the path is chosen from it, not from the local row count)
 bool mb_i8_nt_usable(mb_ctx* ctx, int64_t rows_total, int64_t p, int64_t k);

@@ -962,7 +962,7 @@ int cov_build_impl(mb_ctx* ctx, const mb_kprog* prog, const mb_mat* x, const mb_
         if (done) {
           if (ctx->prof_on)   // algorithmic bytes: K written once, both inputs read once
             ctx->prof_work[MB_PROF_COV] += 8.0 * ((double)x->rows * y->rows + (double)x->cols * ((double)x->rows + y->rows));
-          return 0;
+          return mb_i8_check(ctx);   // protocol time-out / non-finite operand flag (one stream sync per K1 call)
         }
       }
     }
@@ -1124,7 +1124,10 @@ extern "C" int mb_nn_distances(mb_ctx* ctx, const mb_mat* x, const mb_mat* all, 
   int64_t* idx_dev = nullptr;
   MB_CUDA(mb_dev_malloc(ctx, (void**)&idx_dev, sizeof(int64_t) * n));
   int rc = 0;
-  {
+  // tensor-core route (mb_cov_i8.cu, exact int8 digit-slice contraction + running-minimum epilogue): D <= 64, large shapes
+  bool done_i8 = false;
+  rc = mb_cov_i8_build(ctx, MB_K_DISTANCE, 1.0, x, all, nullptr, (int)x->cols, dist->p, 1, &done_i8, self_offset, idx_dev);
+  if (rc == 0 && !done_i8) {
     Plan plan;
     rc = prepare(ctx, &prog, x, all, &plan);
     bool done = false;
@@ -1151,16 +1154,17 @@ extern "C" int mb_nn_distances(mb_ctx* ctx, const mb_mat* x, const mb_mat* all, 
         if (!done) { mb_set_error("mb_nn_distances: launch failed"); rc = -1; }
       }
     }
-    if (rc == 0) {
-      int grid = (int)min((int64_t)ctx->n_sm * 8, ceil_div64(n, 8));
-      nn_exact_kernel<<<grid, 256, 0, ctx->stream>>>(x->p, n, all->p, (int)x->cols, idx_dev, dist->p);
-      ctx->launches++;
-      if (idx_host) cudaMemcpyAsync(idx_host, idx_dev, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
-    }
+  }
+  if (rc == 0) {
+    int grid = (int)min((int64_t)ctx->n_sm * 8, ceil_div64(n, 8));
+    nn_exact_kernel<<<grid, 256, 0, ctx->stream>>>(x->p, n, all->p, (int)x->cols, idx_dev, dist->p);
+    ctx->launches++;
+    if (idx_host) cudaMemcpyAsync(idx_host, idx_dev, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
   }
   cudaStreamSynchronize(ctx->stream);
   cudaFree(idx_dev);
   if (rc == 0 && cudaGetLastError() != cudaSuccess) { mb_set_error("mb_nn_distances: kernel failed"); rc = -1; }
+  if (rc == 0 && done_i8) rc = mb_i8_check(ctx);
   return rc;
 }
 

@@ -192,16 +192,21 @@ struct CovI8Args {
   double* out;
   int64_t ldo;
   int vec;                // out is 16-byte aligned and ldo even: 16-byte stores
+  int64_t self_offset;    // NN mode: column r + self_offset is the cell itself and is skipped
+  int64_t* nn_idx;        // NN mode: index of the nearest column per row (out receives the squared distance)
   int* status;
 };
+enum { I8_STORE = 0, I8_NNMIN = 1 };
 
-template <int KIND>
+template <int KIND, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 cov_i8_kernel(const CovI8Args a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t x_full, x_empty, y_full[NYB], y_empty[NYB], t_full, t_empty;
   __shared__ uint32_t tmem_base_sh;
   __shared__ double tab[64];
+  __shared__ double nn_val[MODE == I8_NNMIN ? NEPI / 4 : 1][MODE == I8_NNMIN ? TM : 1];
+  __shared__ int64_t nn_col[MODE == I8_NNMIN ? NEPI / 4 : 1][MODE == I8_NNMIN ? TM : 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int xbytes = a.ksteps * XKSTEP, ybytes = a.ksteps * YKSTEP + YCONST;
   unsigned char* xs = smem;
@@ -309,6 +314,8 @@ cov_i8_kernel(const CovI8Args a) {
       const double xn = (gi < a.n) ? a.xnorm[gi] + a.eps_scaled : 0.0;
       // 2 x.y = H 256^6 sx sy 2: fold the constant factors into the row scale
       const double sx = (gi < a.n) ? -2.0 * a.xscale[gi] * (double)(1LL << (DB * (NS - 1))) : 0.0;
+      double best = __longlong_as_double(0x7ff0000000000000LL);   // NN mode: running minimum over this thread's columns
+      int64_t best_col = -1;
       for (int64_t jt = 0; jt < n_tiles && ok; jt++, it++) {
         const int s = (int)(it % NYB);
         const uint32_t par = (uint32_t)(it & 1);
@@ -335,32 +342,63 @@ cov_i8_kernel(const CovI8Args a) {
         // column constants of this tile (shared memory, broadcast reads), then the covariance
         const double* cst = reinterpret_cast<const double*>(ys + (size_t)s * ybytes + (size_t)a.ksteps * YKSTEP);
         ok = ok && mbar_wait(&y_full[s], (uint32_t)((it / NYB) & 1), a.status);   // visibility of the constants
-        // 8 columns at a time: evaluate and store (a thread owns 16 consecutive columns of ONE row: 128 bytes)
-        double* orow = a.out + gi * a.ldo + jt * TN + c0;
+        if (MODE == I8_NNMIN) {
+          // exact nearest neighbour: running minimum of xn + yn - 2 x.y over every column but the cell itself; columns
+          // come in increasing order, so `<` keeps the lowest index among equal distances
 #pragma unroll
-        for (int h = 0; h < EC; h += 8) {
-          double val[8];
-#pragma unroll
-          for (int e = 0; e < 8; e++) {
-            const double yn = cst[c0 + h + e], sy = cst[TN + c0 + h + e];
-            const double sq = fma(H[h + e] * sx, sy, xn + yn);            // xn + yn - 2 x.y (+ eps)
-            val[e] = eval_scaled<KIND>(sq, tab);
+          for (int e = 0; e < EC; e++) {
+            const int64_t gj = jt * TN + c0 + e;
+            const double sq = fma(H[e] * sx, cst[TN + c0 + e], xn + cst[c0 + e]);
+            if (gj < a.m && gj != gi + a.self_offset && sq < best) { best = sq; best_col = gj; }
           }
-          if (gi < a.n) {
+        } else {
+        // 8 columns at a time: evaluate and store (a thread owns 16 consecutive columns of ONE row: 128 bytes)
+          double* orow = a.out + gi * a.ldo + jt * TN + c0;
 #pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-              const int64_t gj = jt * TN + c0 + h + e;
-              if (gj + 1 < a.m && a.vec) {
-                *reinterpret_cast<double2*>(orow + h + e) = make_double2(val[e], val[e + 1]);
-              } else {
-                if (gj < a.m) orow[h + e] = val[e];
-                if (gj + 1 < a.m) orow[h + e + 1] = val[e + 1];
+          for (int h = 0; h < EC; h += 8) {
+            double val[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+              const double yn = cst[c0 + h + e], sy = cst[TN + c0 + h + e];
+              const double sq = fma(H[h + e] * sx, sy, xn + yn);            // xn + yn - 2 x.y (+ eps)
+              val[e] = eval_scaled<KIND>(sq, tab);
+            }
+            if (gi < a.n) {
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) {
+                const int64_t gj = jt * TN + c0 + h + e;
+                if (gj + 1 < a.m && a.vec) {
+                  *reinterpret_cast<double2*>(orow + h + e) = make_double2(val[e], val[e + 1]);
+                } else {
+                  if (gj < a.m) orow[h + e] = val[e];
+                  if (gj + 1 < a.m) orow[h + e + 1] = val[e + 1];
+                }
               }
             }
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&y_empty[s]);          // done with the stage's constants
+      }
+      if (MODE == I8_NNMIN) {
+        // the four warps of a lane quadrant hold the minima over their own 16 columns of every tile: combine them in
+        // column-block order, lowest index first among equal distances (named barrier over the 16 epilogue warps)
+        nn_val[cb][row] = best;
+        nn_col[cb][row] = best_col;
+        asm volatile("bar.sync 1, %0;\n" ::"n"(NEPI * 32) : "memory");
+        if (cb == 0 && gi < a.n) {
+          double v = nn_val[0][row];
+          int64_t c = nn_col[0][row];
+#pragma unroll
+          for (int q = 1; q < NEPI / 4; q++) {
+            const double v2 = nn_val[q][row];
+            const int64_t c2 = nn_col[q][row];
+            if (v2 < v || (v2 == v && c2 >= 0 && (c < 0 || c2 < c))) { v = v2; c = c2; }
+          }
+          a.out[gi * a.ldo] = v;
+          a.nn_idx[gi] = c;
+        }
+        asm volatile("bar.sync 1, %0;\n" ::"n"(NEPI * 32) : "memory");
       }
     }
   }
@@ -369,16 +407,20 @@ cov_i8_kernel(const CovI8Args a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
-template <int KIND>
+template <int KIND, int MODE>
 int launch_cov_i8(mb_ctx* ctx, const CovI8Args& a, size_t smem) {
   static bool configured = false;
   if (!configured) {
-    MB_CUDA(cudaFuncSetAttribute(cov_i8_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MB_CUDA((cudaFuncSetAttribute(cov_i8_kernel<KIND, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
     configured = true;
   }
   const int64_t n_panels = ceil_div64(a.n, TM);
   const int grid = (int)std::min<int64_t>(n_panels, ctx->n_sm);
-  MB_LAUNCH_P(ctx, MB_PROF_COV, cov_i8_kernel<KIND>, grid, NTHREADS, smem, a);
+  if (MODE == I8_NNMIN) {
+    MB_LAUNCH(ctx, (cov_i8_kernel<KIND, MODE>), grid, NTHREADS, smem, a);
+  } else {
+    MB_LAUNCH_P(ctx, MB_PROF_COV, (cov_i8_kernel<KIND, MODE>), grid, NTHREADS, smem, a);
+  }
   return 0;
 }
 
@@ -386,11 +428,15 @@ int launch_cov_i8(mb_ctx* ctx, const CovI8Args& a, size_t smem) {
 
 // K(i, j) = k_kind(c |x_i - y_j|) for one exponential-family leaf over the columns `dims` (NULL: the first d columns).
 // *done = false when the shape is outside this kernel (d > 64, tiny problems): the caller falls back to the DMMA kernel.
+// kind == MB_K_DISTANCE: exact nearest-neighbour search instead (c = 1): out(i) = min_j |x_i - y_j|^2 over j != i +
+// self_offset, nn_idx(i) its index (device pointer).
 int mb_cov_i8_build(mb_ctx* ctx, int kind, double c, const mb_mat* x, const mb_mat* y, const int* dims_host, int d,
-                    double* out, int64_t ldo, bool* done) {
+                    double* out, int64_t ldo, bool* done, int64_t self_offset, int64_t* nn_idx) {
   *done = false;
   if (ctx->opt_cov_i8 == 0 || d < 1 || d > 2 * KS) return 0;
-  if (!(kind == MB_K_MATERN32 || kind == MB_K_MATERN52 || kind == MB_K_EXPQUAD || kind == MB_K_EXPONENTIAL)) return 0;
+  if (!(kind == MB_K_MATERN32 || kind == MB_K_MATERN52 || kind == MB_K_EXPQUAD || kind == MB_K_EXPONENTIAL ||
+        (kind == MB_K_DISTANCE && nn_idx)))
+    return 0;
   const int64_t n = x->rows, m = y->rows;
   if (ctx->opt_cov_i8 != 2 && (n < 4096 || m < 256)) return 0;
   if (n == 0 || m == 0) return 0;
@@ -429,17 +475,20 @@ int mb_cov_i8_build(mb_ctx* ctx, int kind, double c, const mb_mat* x, const mb_m
   a.n = n;
   a.m = m;
   a.ksteps = ksteps;
-  a.eps_scaled = 1e-12 * c * c;
+  a.eps_scaled = (kind == MB_K_DISTANCE) ? 0.0 : 1e-12 * c * c;
+  a.self_offset = self_offset;
+  a.nn_idx = nn_idx;
   a.out = out;
   a.ldo = ldo;
   a.vec = ((ldo & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
   a.status = ctx->i8_status;
   const size_t smem = (size_t)xbytes + (size_t)NYB * ybytes;
   switch (kind) {
-    case MB_K_MATERN32: MB_TRY(launch_cov_i8<MB_K_MATERN32>(ctx, a, smem)); break;
-    case MB_K_MATERN52: MB_TRY(launch_cov_i8<MB_K_MATERN52>(ctx, a, smem)); break;
-    case MB_K_EXPQUAD: MB_TRY(launch_cov_i8<MB_K_EXPQUAD>(ctx, a, smem)); break;
-    default: MB_TRY(launch_cov_i8<MB_K_EXPONENTIAL>(ctx, a, smem)); break;
+    case MB_K_MATERN32: MB_TRY((launch_cov_i8<MB_K_MATERN32, I8_STORE>(ctx, a, smem))); break;
+    case MB_K_MATERN52: MB_TRY((launch_cov_i8<MB_K_MATERN52, I8_STORE>(ctx, a, smem))); break;
+    case MB_K_EXPQUAD: MB_TRY((launch_cov_i8<MB_K_EXPQUAD, I8_STORE>(ctx, a, smem))); break;
+    case MB_K_DISTANCE: MB_TRY((launch_cov_i8<MB_K_DISTANCE, I8_NNMIN>(ctx, a, smem))); break;
+    default: MB_TRY((launch_cov_i8<MB_K_EXPONENTIAL, I8_STORE>(ctx, a, smem))); break;
   }
   *done = true;
   return 0;

@@ -634,3 +634,30 @@ def test_int8_gemm_issue_variants_give_identical_bits(be):
                 assert np.array_equal(T, ref_t), f"TRSM differs with i8_issuers={iss}"
     finally:
         be.set_option("i8_issuers", 4)
+
+
+@pytest.mark.parametrize("n,d,forced", [(2, 1, True), (50, 3, True), (1000, 10, True), (3000, 50, True), (777, 64, True),
+                                        (20011, 50, False), (9000, 33, False)])
+def test_nn_distances_on_int8_digit_slices(be, n, d, forced):
+    """Exact nearest neighbour through the tcgen05 int8 digit-slice kernel (running-minimum epilogue): indices bit-exact
+    against scikit-learn's brute-force search, duplicates and ragged shapes included; forced at small sizes."""
+    if be.name != "cuda":
+        pytest.skip("the int8 digit-slice path exists in the CUDA library only")
+    from sklearn.neighbors import NearestNeighbors
+
+    x = np.random.default_rng(n + d).random((n, d))
+    if n >= 50:
+        x[7] = x[3]                                           # a duplicate: distance 0, lowest index wins
+    be.set_option("cov_i8", 2 if forced else 1)
+    try:
+        dist, idx = be.nn_distances(x, return_index=True)
+    finally:
+        be.set_option("cov_i8", 1)
+    rd, ri = NearestNeighbors(n_neighbors=2, algorithm="brute").fit(x).kneighbors(x)
+    exact = np.sqrt(np.sum((x - x[idx]) ** 2, axis=1))
+    np.testing.assert_allclose(dist, rd[:, 1], rtol=1e-13, atol=1e-300)
+    np.testing.assert_allclose(dist, exact, rtol=1e-13, atol=1e-300)
+    same = idx == ri[:, 1]
+    # scikit-learn breaks exact ties (duplicated points) by its own order: accept any index at the identical distance
+    assert np.all(same | (np.abs(exact - rd[:, 1]) <= 1e-13 * np.maximum(rd[:, 1], 1e-300)))
+    assert np.count_nonzero(~same) <= 2                      # only the duplicated pair can differ
