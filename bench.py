@@ -588,6 +588,10 @@ def run_b200(args):
             "launches": n_i8, "ms_per_step": ms_i8 / n_fit_steps, "share": ms_i8 / ms,
             "achieved_f64_equiv_TFLOPs": flops_i8 / (ms_i8 * 1e-3) / 1e12 if ms_i8 else None},
     }
+    n_eg, ms_eg, _ = prof.get("eigh", (0, 0.0, 0.0))
+    if n_eg:
+        kernels["syevd (cuSOLVER Dsyevd: LIBRARY call, the Nystroem path's two M x M eigh)"] = {
+            "launches": n_eg, "ms_per_step": ms_eg / n_fit_steps, "share": ms_eg / ms}
     n_evals = max(1, int(np.sum(nfev)))
     per_eval = {"evaluations_per_step": float(np.mean(nfev)),
                 "k5_kernel_ms_per_eval": ms_lg / max(n_lg, 1),

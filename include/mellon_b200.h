@@ -103,7 +103,7 @@ int mb_timer_stop(mb_ctx* ctx, int slot, double* ms);
  * HBM-bound classes, flops for the GEMM class).  Classes: 0 = K1 covariance build (x != y),
  * 1 = K7 covariance mat-vec, 2 = FP64 GEMM tiles (K3/K4/K2 updates), 3 = K5/K6 fused objective
  * pass, 4 = everything else that is timed (the symmetric landmark covariance K_MM), 5 = int8 digit-slice GEMMs
- * on tcgen05 (work: float64-equivalent flops). */
+ * on tcgen05 (work: float64-equivalent flops), 6 = the cuSOLVER Dsyevd library call of the Nystroem path. */
 int mb_prof_enable(mb_ctx* ctx, int on);
 int mb_prof_reset(mb_ctx* ctx);
 int mb_prof_read(mb_ctx* ctx, int cls, int64_t* count, double* ms, double* work);

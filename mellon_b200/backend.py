@@ -218,7 +218,7 @@ class CudaBackend:
         nat.check(self.lib.mb_timer_stop(self.ctx, slot, C.byref(ms)))
         return ms.value
 
-    PROF_CLASSES = {"cov": 0, "matvec": 1, "gemm": 2, "lossgrad": 3, "other": 4, "gemm_i8": 5}
+    PROF_CLASSES = {"cov": 0, "matvec": 1, "gemm": 2, "lossgrad": 3, "other": 4, "gemm_i8": 5, "eigh": 6}
 
     def prof_enable(self, on=True):
         nat.check(self.lib.mb_prof_enable(self.ctx, int(bool(on))), "mb_prof_enable")

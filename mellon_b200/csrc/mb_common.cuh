@@ -68,7 +68,7 @@ int mb_i8_gemm_nt(mb_ctx* ctx, int64_t n, int64_t p, int64_t k, double alpha, co
 
 // kernel classes for the in-library stopwatch (mb_prof_*): CUDA events around each launch
 enum { MB_PROF_COV = 0, MB_PROF_MATVEC = 1, MB_PROF_GEMM = 2, MB_PROF_LOSSGRAD = 3, MB_PROF_OTHER = 4,
-       MB_PROF_I8 = 5, MB_PROF_NCLS = 6 };
+       MB_PROF_I8 = 5, MB_PROF_EIGH = 6, MB_PROF_NCLS = 7 };
 
 struct mb_prof_span {
   int cls;

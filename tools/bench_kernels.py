@@ -1,6 +1,6 @@
 """Kernel-level timings on one GPU (CUDA events on the library stream, best of 3 after a warm-up):
 
-    python tools/bench_kernels.py [N=262144] [M=5000] [D=50]
+    python tools/bench_kernels.py [N=262144] [M=5000] [D=50] [k1]        (k1: the K1 lines only)
 
 K1 (fused distance + covariance build) on the int8 digit-slice kernel and on the FP64 DMMA kernel, K4 Gram and K3 TRSM
 with the int8 slices on and off.  Prints ms, algorithmic GB/s (K1) and float64-equivalent TF/s (K3 / K4)."""
@@ -46,6 +46,8 @@ for name, opt in (("int8 slices (tcgen05)", 1), ("FP64 DMMA", 0)):
     print(f"K1 {name:24s} N={N} M={M} D={D}: call {ms:8.3f} ms (kernel alone {ms_k / max(n_l, 1):8.3f} ms) = {alg / ms / 1e6:7.1f} GB/s "
           f"algorithmic incl. pack, {alg / (ms_k / max(n_l, 1)) / 1e6:7.1f} GB/s kernel only; scaled to N=1e6: {ms * 1e6 / N:6.2f} ms")
 be.set_option("cov_i8", 1)
+if len(sys.argv) > 4 and sys.argv[4] == "k1":
+    sys.exit(0)
 
 K = be.cov(cov, xd, xud, sharded=True)
 Lp, info = be.cov_chol(cov, xu, 1e-6)
