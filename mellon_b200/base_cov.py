@@ -241,9 +241,11 @@ class Covariance(ABC):
             raise ValueError("The passed dict does not seem to define a covariance kernel.")
         clsname = state["metadata"]["classname"]
         module_name = state["metadata"]["module_name"]
-        Sub = _REGISTRY.get(clsname)
+        # files written by the reference name its own modules ("mellon.cov", ...): same classes here; a user class that
+        # only shares its NAME with a stock kernel is imported from the module it names
+        ours = str(module_name).split(".")[0] in ("mellon", "mellon_b200")
+        Sub = _REGISTRY.get(clsname) if ours else None
         if Sub is None:
-            # files written by the reference name its own modules ("mellon.cov", ...)
             Sub = getattr(import_module(module_name), clsname)
         instance = Sub.__new__(Sub)
         instance.__setstate__(state)

@@ -38,22 +38,28 @@ def _central_gradient(f, x, cols, h_rel=1e-5):
     """d f / d x[:, j] for j in ``cols`` by central differences; ``f`` maps (n, d) -> (n,).  Each column costs two
     evaluations of the (device) predictor mean."""
     x = np.asarray(x, dtype=float)
-    out = np.empty((x.shape[0], len(cols)))
+    out = None
     for a, j in enumerate(cols):
         h = h_rel * max(1.0, float(np.max(np.abs(x[:, j])))) if x.shape[0] else h_rel
         e = np.zeros(x.shape[1])
         e[j] = h
-        out[:, a] = (np.asarray(f(x + e)) - np.asarray(f(x - e))) / (2.0 * h)
-    return out
+        diff = (np.asarray(f(x + e)) - np.asarray(f(x - e))) / (2.0 * h)
+        if out is None:   # (n, k) for a scalar mean, (n, p, k) for a multi-output one (FunctionEstimator with y of shape (n, p))
+            out = np.empty(diff.shape + (len(cols),))
+        out[..., a] = diff
+    return out if out is not None else np.empty((x.shape[0], 0))
 
 
 def _central_hessian(f, x, cols, h_rel=1e-4):
     """Second derivatives over the columns ``cols`` by central differences: (n, len(cols), len(cols))."""
     x = np.asarray(x, dtype=float)
     k = len(cols)
-    out = np.empty((x.shape[0], k, k))
     hs = [h_rel * max(1.0, float(np.max(np.abs(x[:, j])))) if x.shape[0] else h_rel for j in cols]
     f0 = np.asarray(f(x))
+    if f0.ndim != 1:
+        raise NotImplementedError("hessian / hessian_log_determinant of a multi-output predictor (a FunctionEstimator fitted "
+                                  "with y of shape (n, p)) are not provided; take them per output column.")
+    out = np.empty((x.shape[0], k, k))
     for a, j in enumerate(cols):
         ej = np.zeros(x.shape[1])
         ej[j] = hs[a]
@@ -319,10 +325,17 @@ class Predictor(ABC):
             data = data_dict["data"]
             data["n_obs"] = data.get("n_obs", None)
             data["_state_variables"] = data.get("_state_variables", set(data.keys()) - {"n_input_features"})
-        # predictors written by the reference name its module ("mellon.conditional"): same classes here
+        # predictors written by the reference name its module ("mellon.conditional"): same classes here.  The
+        # class-name shortcut only applies to the reference's and this package's own modules: a user class that merely
+        # shares a name with a stock one is imported from the module it names.
         from . import conditional
 
-        Sub = getattr(conditional, clsname, None)
+        ours = module_name.split(".")[0] in ("mellon", "mellon_b200")
+        if ours and clsname.startswith("Exp"):
+            raise NotImplementedError(
+                f"{clsname} (the reference's exp-log predictor family, mellon/conditional.py) is outside the path "
+                "mellon_b200 implements; load this file with mellon.")
+        Sub = getattr(conditional, clsname, None) if ours else None
         if Sub is None:
             Sub = getattr(import_module(module_name), clsname)
         instance = Sub.__new__(Sub)

@@ -114,3 +114,24 @@ def test_distance_grad_and_jax_config_shims(be):
     mb.util.set_jax_config()
     with pytest.raises(ValueError):
         mb.util.set_jax_config(enable_x64=False)
+
+
+def test_gradient_of_a_multi_output_predictor_and_named_refusals(be):
+    """the numerical gradient of a multi-output mean (FunctionEstimator with y of shape (n, p)) has
+    shape (n, p, d); the Hessian is refused by name; a reference-written exp-log predictor is refused by name; a user
+    covariance class that shares a stock NAME is loaded from its own module."""
+    rng = np.random.default_rng(4)
+    X = rng.random((150, 2))
+    Y = np.stack([np.sin(3 * X[:, 0]), X[:, 1] ** 2], axis=1)
+    fe = mb.FunctionEstimator(n_landmarks=0, ls=0.5, sigma=0.05).fit(X, Y)
+    Q = rng.random((7, 2))
+    g = fe.predict.gradient(Q)
+    assert g.shape == (7, 2, 2)
+    h = 1e-5
+    fd = (fe.predict(Q + [h, 0]) - fe.predict(Q - [h, 0])) / (2 * h)
+    np.testing.assert_allclose(g[:, :, 0], fd, rtol=1e-4, atol=1e-6)
+    with pytest.raises(NotImplementedError, match="multi-output"):
+        fe.predict.hessian(Q)
+    with pytest.raises(NotImplementedError, match="ExpLandmarksConditional"):
+        mb.Predictor.from_dict({"metadata": {"classname": "ExpLandmarksConditional", "module_name": "mellon.conditional",
+                                             "module_version": "1.7.1"}, "data": {}})
