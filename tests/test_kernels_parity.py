@@ -661,4 +661,5 @@ def test_nn_distances_on_int8_digit_slices(be, n, d, forced):
     same = idx == ri[:, 1]
     # scikit-learn breaks exact ties (duplicated points) by its own order: accept any index at the same distance
     assert np.all(same | (np.abs(exact - rd[:, 1]) <= 1e-6))
-    assert np.count_nonzero(~same) <= 2                      # only the duplicated pair can differ
+    # rows whose nearest neighbour IS the duplicated point see a two-way tie as well: a handful of rows at most
+    assert np.count_nonzero(~same) <= 8
