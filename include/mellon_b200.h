@@ -122,6 +122,9 @@ int mb_flush_l2(mb_ctx* ctx);
  *   "cov_i8"   0 = K1 always on the FP64 DMMA kernel; 1 (default) = one exponential-family leaf with D <= 64, >= 4096
  *              cells and >= 256 landmarks on the tcgen05 kind::i8 digit-slice kernel; 2 = at every size (tests)
  *   "i8_issuers" MMA-issuing warps of the int8 GEMM kernels: 1, 2 or 4 (default 4)
+ *   "i8_overlap" 1 = the digit pack of the next slab / chunk runs on a side stream under the int8 GEMM of the current
+ *              one (same kernels, same bits; measured gain 0-2 %: both go through the L1 / shared-memory port);
+ *              0 (default) = in sequence on the library stream
  *   "graph"    0 = launch the Cholesky on the stream instead of replaying its CUDA graph
  *   "i8"       0 = every FP64 product on the DMMA tiles; 1 (default) = the large products on tcgen05 kind::i8 digit
  *              slices: Gram matrices with chunks >= 2048 cells and r >= 512, TRSM updates / tall GEMMs with >= 8192

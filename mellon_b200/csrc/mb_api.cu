@@ -93,6 +93,15 @@ extern "C" int mb_ctx_destroy(mb_ctx* c) {
   if (c->i8_ws) cudaFree(c->i8_ws);
   if (c->i8_tiles) cudaFree(c->i8_tiles);
   if (c->i8_status) cudaFree(c->i8_status);
+  if (c->i8_side) {
+    cudaStreamSynchronize(c->i8_side);
+    cudaStreamDestroy(c->i8_side);
+    cudaEventDestroy(c->i8_ev_start);
+    for (int b = 0; b < 2; b++) {
+      cudaEventDestroy(c->i8_ev_packed[b]);
+      cudaEventDestroy(c->i8_ev_free[b]);
+    }
+  }
   if (c->trsm_ws) cudaFree(c->trsm_ws);
   mb_invalidate_graphs(c);
   if (c->potrf_buf) cudaFree(c->potrf_buf);
@@ -224,6 +233,7 @@ extern "C" int mb_set_option(mb_ctx* c, const char* key, int value) {
   else if (!strcmp(key, "i8")) c->opt_i8 = value;
   else if (!strcmp(key, "cov_i8")) c->opt_cov_i8 = value;
   else if (!strcmp(key, "i8_issuers")) c->opt_i8_issuers = value;
+  else if (!strcmp(key, "i8_overlap")) c->opt_i8_overlap = value;
   else MB_CHECK(false, "mb_set_option: unknown key %s", key);
   return 0;
 }

@@ -56,6 +56,9 @@ int mb_axpy_raw(mb_ctx* ctx, double* dst, const double* src, int64_t count);
 // int8 digit-slice Gram of one block of cells (mb_i8.cu): out (r x r dense, tiles on / below the diagonal) = A^T A
 bool mb_i8_gram_usable(mb_ctx* ctx, int64_t rows, int64_t r);
 int mb_i8_gram_leaf(mb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t r, double* out);
+// a sequence of Gram leaves over one factor that is complete on the main stream at `begin`: their packs may run ahead
+int mb_i8_gram_begin(mb_ctx* ctx);
+void mb_i8_gram_end(mb_ctx* ctx);
 int mb_i8_check(mb_ctx* ctx);
 // K1 on int8 digit slices (mb_cov_i8.cu); *done = false: shape / kind outside that kernel
 int mb_cov_i8_build(mb_ctx* ctx, int kind, double c, const mb_mat* x, const mb_mat* y, const int* dims_host, int d,
@@ -111,6 +114,13 @@ struct mb_ctx {
   int64_t i8_tiles_r = -1;
   int i8_ntiles = 0;
   int* i8_status = nullptr;
+  // option "i8_overlap": the pack of the NEXT slab / chunk runs on a side stream under the GEMM of the current one (two
+  // operand buffers, events for the hand-offs)
+  cudaStream_t i8_side = nullptr;
+  cudaEvent_t i8_ev_start = nullptr, i8_ev_packed[2] = {nullptr, nullptr}, i8_ev_free[2] = {nullptr, nullptr};
+  int i8_seq = -1;       // Gram leaves since mb_i8_gram_begin (-1: no sequence open, leaves run on the main stream)
+  size_t i8_seq_one = 0; // size of one operand buffer of the open sequence
+  int opt_i8_overlap = 0;  // 1 = packs of the next slab / chunk on the side stream (measured: no gain, see mb_i8.cu)
   int opt_cov_i8 = 1;    // 1 = K1 of one exponential-family leaf on tcgen05 int8 digit slices (large shapes), 2 = always, 0 = DMMA kernel
   int opt_i8_issuers = 4;  // MMA-issuing warps of the int8 GEMM kernels (1, 2 or 4)
   int opt_i8 = 1;        // 1 = Gram products of large factors on tcgen05 kind::i8 digit slices, 0 = FP64 DMMA tiles
@@ -165,6 +175,14 @@ void mb_set_error(const char* fmt, ...);
 #define MB_LAUNCH(ctx, kernel, grid, block, smem, ...)                             \
   do {                                                                             \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);               \
+    (ctx)->launches++;                                                             \
+    MB_CUDA(cudaGetLastError());                                                   \
+  } while (0)
+
+// launch on another stream of the context (the int8 side stream)
+#define MB_LAUNCH_ON(ctx, strm, kernel, grid, block, smem, ...)                   \
+  do {                                                                             \
+    kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);                      \
     (ctx)->launches++;                                                             \
     MB_CUDA(cudaGetLastError());                                                   \
   } while (0)

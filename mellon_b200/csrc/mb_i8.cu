@@ -31,7 +31,6 @@ namespace {
 
 constexpr int DB = 8;                          // digit width
 constexpr int NS = 7;                          // digit slices per value: 54-bit fixed point
-constexpr long long DHALF = 1LL << (DB - 1), DMASK = (1LL << DB) - 1;
 constexpr int KS = 32;                         // cells per k-step (one kind::i8 MMA: K = 32)
 constexpr int TA = 128, TB = 64;               // output tile: 128 rows (A panel) x 64 columns (B panel)
 constexpr int ASLICE = 2 * TA * 16, ABLOCK = NS * ASLICE;   // 4 KB per slice, 28 KB per (A panel, k-step)
@@ -42,6 +41,49 @@ constexpr int SMEM_TOTAL = NST * (ABLOCK + BBLOCK);         // 168 KB
 constexpr int KC = 16384;                      // cells per group: |G_g| <= 7 * 2^28 < 2^31
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- float64 -> digit slices ------------------------------------------------------------------------------------
+// q = rint(v 2^(54 - E)), |q| <= 2^54.  Adding 128 to every balanced digit turns them into the plain base-256 digits of
+// the non-negative number q + sum_t 128 256^t, so the digits are the BYTES of (q + DBIAS) ^ DBIAS (the xor takes the
+// 128 off again, in two's complement): byte b is slice NS - 1 - b.  One add and one xor instead of a 7-step carry loop.
+constexpr unsigned long long DBIAS = 0x0080808080808080ull;
+
+__device__ __noinline__ long long fixed54_tiny(double v, int sh) { return llrint(ldexp(v, sh)); }
+
+// q[c] = rint(x[c] 2^(54 - E)) for 16 values with one exponent.  The scale 2^(54 - E) is a double (built from its
+// exponent bits; the product is exact) unless the whole row / column is below 2^-960: ldexp then, same integers.
+__device__ __forceinline__ void fixed54x16(const double (&x)[16], int E, long long (&q)[16]) {
+  if (E >= -960) {
+    const double s = __longlong_as_double((long long)(1023 + 54 - E) << 52);
+#pragma unroll
+    for (int c = 0; c < 16; c++) q[c] = __double2ll_rn(x[c] * s);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 16; c++) q[c] = fixed54_tiny(x[c], 54 - E);
+  }
+}
+
+// digits of four values -> one 32-bit word per slice, value c in byte c (the operand layout's 4 consecutive k)
+__device__ __forceinline__ void digits_of4(const long long* q, uint32_t (&w)[NS]) {
+  uint32_t lo[4], hi[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const unsigned long long v = ((unsigned long long)q[c] + DBIAS) ^ DBIAS;
+    lo[c] = (uint32_t)v;
+    hi[c] = (uint32_t)(v >> 32);
+  }
+  uint32_t a = __byte_perm(lo[0], lo[1], 0x5140), b = __byte_perm(lo[2], lo[3], 0x5140);   // bytes 0, 1 of the pair
+  w[6] = __byte_perm(a, b, 0x5410);
+  w[5] = __byte_perm(a, b, 0x7632);
+  a = __byte_perm(lo[0], lo[1], 0x7362), b = __byte_perm(lo[2], lo[3], 0x7362);            // bytes 2, 3
+  w[4] = __byte_perm(a, b, 0x5410);
+  w[3] = __byte_perm(a, b, 0x7632);
+  a = __byte_perm(hi[0], hi[1], 0x5140), b = __byte_perm(hi[2], hi[3], 0x5140);            // bytes 4, 5
+  w[2] = __byte_perm(a, b, 0x5410);
+  w[1] = __byte_perm(a, b, 0x7632);
+  a = __byte_perm(hi[0], hi[1], 0x7362), b = __byte_perm(hi[2], hi[3], 0x7362);            // byte 6 (byte 7 is zero)
+  w[0] = __byte_perm(a, b, 0x5410);
+}
 
 // ---- column scales: max |A_ij| over the group, as the bit pattern of a non-negative double (ordered like uint64) ----
 __global__ void colmax_kernel(const double* __restrict__ A, int64_t rows, int64_t r, int64_t ld,
@@ -72,20 +114,21 @@ pack_cols_kernel(const double* __restrict__ A, int64_t rows, int64_t r, int64_t 
   } else if (ks == 0 && chunk == 0) {
     scale[j] = 0.0;
   }
-  uint32_t dig[NS][4];
-#pragma unroll
-  for (int t = 0; t < NS; t++) dig[t][0] = dig[t][1] = dig[t][2] = dig[t][3] = 0u;
+  double x[16];
 #pragma unroll
   for (int c = 0; c < 16; c++) {
     const int64_t i = ks * KS + chunk * 16 + c;
-    long long q = 0;
-    if (j < r && i < rows) q = llrint(ldexp(A[i * ld + j], 54 - E));
+    x[c] = (j < r && i < rows) ? A[i * ld + j] : 0.0;
+  }
+  long long q[16];
+  fixed54x16(x, E, q);
+  uint32_t dig[NS][4];
 #pragma unroll
-    for (int t = NS - 1; t >= 0; t--) {
-      const long long d = ((q + DHALF) & DMASK) - DHALF;     // balanced digit in [-128, 127]
-      q = (q - d) >> DB;
-      dig[t][c >> 2] |= (uint32_t)(uint8_t)(int8_t)d << (8 * (c & 3));
-    }
+  for (int g = 0; g < 4; g++) {
+    uint32_t w[NS];
+    digits_of4(q + 4 * g, w);
+#pragma unroll
+    for (int t = 0; t < NS; t++) dig[t][g] = w[t];
   }
   int8_t* ab = Ad + (pa * nks + ks) * (int64_t)ABLOCK;
   int8_t* bb = Bd + ((2 * pa + (col >> 6)) * nks + ks) * (int64_t)BBLOCK;
@@ -400,20 +443,30 @@ pack_rows_kernel(const double* __restrict__ X, int64_t rows, int64_t k, int64_t 
   const int row = threadIdx.x % P, chunk = threadIdx.x / P;
   const int64_t i = panel * P + row;
   const int E = (i < rows) ? expo[i] : 0;
+  const int64_t k0 = ks * KS + chunk * 16;
+  const double* src = X + i * ld + k0;
+  double x[16];
+  if (i < rows && k0 + 16 <= k && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    // 16-byte loads: the 128 B of a thread are one cache line, fetched with 8 requests instead of 16
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(src) + c);
+      x[2 * c] = v.x;
+      x[2 * c + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 16; c++) x[c] = (i < rows && k0 + c < k) ? src[c] : 0.0;
+  }
+  long long q[16];
+  fixed54x16(x, E, q);
   uint32_t dig[NS][4];
 #pragma unroll
-  for (int t = 0; t < NS; t++) dig[t][0] = dig[t][1] = dig[t][2] = dig[t][3] = 0u;
+  for (int g = 0; g < 4; g++) {
+    uint32_t w[NS];
+    digits_of4(q + 4 * g, w);
 #pragma unroll
-  for (int c = 0; c < 16; c++) {
-    const int64_t kk = ks * KS + chunk * 16 + c;
-    long long q = 0;
-    if (i < rows && kk < k) q = llrint(ldexp(X[i * ld + kk], 54 - E));
-#pragma unroll
-    for (int t = NS - 1; t >= 0; t--) {
-      const long long d = ((q + DHALF) & DMASK) - DHALF;
-      q = (q - d) >> DB;
-      dig[t][c >> 2] |= (uint32_t)(uint8_t)(int8_t)d << (8 * (c & 3));
-    }
+    for (int t = 0; t < NS; t++) dig[t][g] = w[t];
   }
   int8_t* blk = Xd + (panel * nks + ks) * (int64_t)(NS * 2 * P * 16);
 #pragma unroll
@@ -524,12 +577,62 @@ int ensure_ws(mb_ctx* ctx, size_t bytes) {
   return 0;
 }
 
+
+// side stream + events, created on first use; false while the main stream is being captured into a graph
+int side_setup(mb_ctx* ctx, bool* usable) {
+  *usable = false;
+  if (!ctx->opt_i8_overlap) return 0;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(ctx->stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return 0;
+  }
+  if (!ctx->i8_side) {
+    int lo = 0, hi = 0;
+    MB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    cudaStream_t sd = nullptr;
+    MB_CUDA(cudaStreamCreateWithPriority(&sd, cudaStreamNonBlocking, hi));   // the packs feed the next GEMM: run them first
+    MB_CUDA(cudaEventCreateWithFlags(&ctx->i8_ev_start, cudaEventDisableTiming));
+    for (int b = 0; b < 2; b++) {
+      MB_CUDA(cudaEventCreateWithFlags(&ctx->i8_ev_packed[b], cudaEventDisableTiming));
+      MB_CUDA(cudaEventCreateWithFlags(&ctx->i8_ev_free[b], cudaEventDisableTiming));
+    }
+    ctx->i8_side = sd;
+  }
+  *usable = true;
+  return 0;
+}
+
+// everything enqueued on the main stream so far (the operands) is visible to the side stream
+int side_fork(mb_ctx* ctx) {
+  MB_CUDA(cudaEventRecord(ctx->i8_ev_start, ctx->stream));
+  MB_CUDA(cudaStreamWaitEvent(ctx->i8_side, ctx->i8_ev_start, 0));
+  return 0;
+}
+
 }  // namespace
 
 bool mb_i8_gram_usable(mb_ctx* ctx, int64_t rows, int64_t r) {
   if (ctx->opt_i8 == 2) return r >= 1 && rows >= 1;   // forced (tests, sanitizer runs on small shapes)
   return ctx->opt_i8 != 0 && r >= 512 && rows >= 2048;
 }
+
+// Open a sequence of Gram leaves over a factor that is complete on the main stream NOW: with "i8_overlap" set, the
+// leaves pack their digits on the side stream into alternating buffers until mb_i8_gram_end, so the (HBM-bound) pack of
+// leaf c + 1 runs under the MMA kernel of leaf c.  Same kernels on the same data: the results do not change.
+// Measured (profiles/bench_kernels_r02.txt (e)): 1-2 % on the Gram, nothing on the TRSM updates - the pack's loads and
+// the MMA operands go through the same L1 / shared-memory port, which is what bounds the MMA kernels - so it is OFF by
+// default and kept as a measured variant.
+int mb_i8_gram_begin(mb_ctx* ctx) {
+  bool usable = false;
+  MB_TRY(side_setup(ctx, &usable));
+  if (!usable) return 0;
+  MB_TRY(side_fork(ctx));
+  ctx->i8_seq = 0;
+  ctx->i8_seq_one = 0;
+  return 0;
+}
+void mb_i8_gram_end(mb_ctx* ctx) { ctx->i8_seq = -1; }
 
 // out (r x r dense; the tiles on and below the diagonal are written) = A^T A for the `rows` x r block at A
 int mb_i8_gram_leaf(mb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int64_t r, double* out) {
@@ -562,29 +665,48 @@ int mb_i8_gram_leaf(mb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int
     MB_CUDA(cudaFuncSetAttribute(gram_i8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     configured = true;
   }
-  // workspace: digits (A and B layouts), scales, column maxima, per-group partial products
+  // workspace: one operand buffer {digits (A and B layouts), scales, column maxima} (two inside a sequence with the
+  // packs on the side stream) + per-group partial products
+  const bool ahead = ctx->i8_seq >= 0;                      // inside mb_i8_gram_begin .. end: packs on the side stream
+  const int buf = ahead ? (ctx->i8_seq & 1) : 0;
+  cudaStream_t ps = ahead ? ctx->i8_side : ctx->stream;
   const size_t a_g = (size_t)npa * nks_max * ABLOCK, b_g = (size_t)npb * nks_max * BBLOCK;
   const size_t part = (ng > 1) ? (size_t)r * r * sizeof(double) : 0;
   auto al = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
   const size_t off_b = al((size_t)ng * a_g), off_s = off_b + al((size_t)ng * b_g),
-               off_m = off_s + al((size_t)ng * rpad * 8), off_p = off_m + al((size_t)ng * rpad * 8),
-               total = off_p + (size_t)ng * part;
+               off_m = off_s + al((size_t)ng * rpad * 8), need = off_m + al((size_t)ng * rpad * 8);
+  // the two buffers keep ONE size over a sequence (the leaves of a tree differ in rows: the last chunk is shorter), or
+  // the second buffer of a small leaf would start inside the first buffer of the large one before it
+  size_t one = need;
+  if (ahead) {
+    if (need > ctx->i8_seq_one) {
+      if (ctx->i8_seq > 0) MB_CUDA(cudaStreamSynchronize(ctx->stream));   // a larger leaf late in a sequence: drain first
+      ctx->i8_seq_one = need;
+    }
+    one = ctx->i8_seq_one;
+  }
+  const size_t nbuf = ahead ? 2 : 1, total = nbuf * one + (size_t)ng * part;
   MB_TRY(ensure_ws(ctx, total));
-  unsigned char* ws = reinterpret_cast<unsigned char*>(ctx->i8_ws);
+  unsigned char* ws = reinterpret_cast<unsigned char*>(ctx->i8_ws) + (size_t)buf * one;
   int8_t* Ad = reinterpret_cast<int8_t*>(ws);
   int8_t* Bd = reinterpret_cast<int8_t*>(ws + off_b);
   double* scale = reinterpret_cast<double*>(ws + off_s);
   unsigned long long* cmax = reinterpret_cast<unsigned long long*>(ws + off_m);
-  double* parts = reinterpret_cast<double*>(ws + off_p);
+  double* parts = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ctx->i8_ws) + nbuf * one);
 
-  MB_CUDA(cudaMemsetAsync(cmax, 0, (size_t)ng * rpad * 8, ctx->stream));
+  if (ahead && ctx->i8_seq >= 2) MB_CUDA(cudaStreamWaitEvent(ps, ctx->i8_ev_free[buf], 0));   // its last reader is done
+  MB_CUDA(cudaMemsetAsync(cmax, 0, (size_t)ng * rpad * 8, ps));
   for (int g = 0; g < ng; g++) {
     const int64_t i0 = (int64_t)g * grows, grw = std::min(grows, rows - i0), nks = ceil_div64(grw, KS);
-    MB_LAUNCH(ctx, colmax_kernel, dim3((unsigned)ceil_div64(r, 128), 64), 128, 0, A + i0 * lda, grw, r, lda,
-              cmax + (int64_t)g * rpad);
-    MB_LAUNCH(ctx, pack_cols_kernel, dim3((unsigned)npa, (unsigned)nks), 256, 0, A + i0 * lda, grw, r, lda,
-              cmax + (int64_t)g * rpad, nks_max, Ad + (size_t)g * a_g, Bd + (size_t)g * b_g, scale + (int64_t)g * rpad,
-              ctx->i8_status);
+    MB_LAUNCH_ON(ctx, ps, colmax_kernel, dim3((unsigned)ceil_div64(r, 128), 64), 128, 0, A + i0 * lda, grw, r, lda,
+                 cmax + (int64_t)g * rpad);
+    MB_LAUNCH_ON(ctx, ps, pack_cols_kernel, dim3((unsigned)npa, (unsigned)nks), 256, 0, A + i0 * lda, grw, r, lda,
+                 cmax + (int64_t)g * rpad, nks_max, Ad + (size_t)g * a_g, Bd + (size_t)g * b_g, scale + (int64_t)g * rpad,
+                 ctx->i8_status);
+  }
+  if (ahead) {
+    MB_CUDA(cudaEventRecord(ctx->i8_ev_packed[buf], ps));
+    MB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->i8_ev_packed[buf], 0));
   }
   GramArgs ga;
   ga.Ad = Ad;
@@ -608,6 +730,10 @@ int mb_i8_gram_leaf(mb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int
   else if (ctx->opt_i8_issuers == 1) MB_LAUNCH_P(ctx, MB_PROF_I8, gram_i8_kernel<1>, ggrid, NT, SMEM_TOTAL, ga);
   else if (ctx->opt_i8_issuers == 2) MB_LAUNCH_P(ctx, MB_PROF_I8, gram_i8_kernel<2>, ggrid, NT, SMEM_TOTAL, ga);
   else MB_LAUNCH_P(ctx, MB_PROF_I8, gram_i8_kernel<4>, ggrid, NT, SMEM_TOTAL, ga);
+  if (ahead) {
+    MB_CUDA(cudaEventRecord(ctx->i8_ev_free[buf], ctx->stream));
+    ctx->i8_seq++;
+  }
   if (ng > 1) {
     const int64_t n = (int64_t)r * r;
     MB_LAUNCH(ctx, sum_groups_kernel, (int)std::min<int64_t>(ceil_div64(n, 256), (int64_t)ctx->n_sm * 16), 256, 0, parts, ng,
@@ -645,28 +771,42 @@ int mb_i8_gemm_nt(mb_ctx* ctx, int64_t n, int64_t p, int64_t k, double alpha, co
   const int64_t SLAB = 65536;
   const int64_t nks = ceil_div64(k, KS), npb = ceil_div64(p, TB), ppad = npb * TB;
   const int64_t slab_rows = std::min(n, SLAB), slab_pad = ceil_div64(slab_rows, TA) * TA;
+  // more than one slab: the pack of slab s + 1 runs on the side stream under the MMA kernel of slab s (two A buffers)
+  bool ahead = false;
+  if (n > SLAB) MB_TRY(side_setup(ctx, &ahead));
+  const int nbuf = ahead ? 2 : 1;
   auto al = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
   const size_t b_bytes = (size_t)npb * nks * BBLOCK, a_bytes = (size_t)(slab_pad / TA) * nks * ABLOCK;
-  const size_t off_a = al(b_bytes), off_sb = off_a + al(a_bytes), off_sa = off_sb + al((size_t)ppad * 8),
-               off_eb = off_sa + al((size_t)slab_pad * 8), off_ea = off_eb + al((size_t)ppad * 4),
-               total = off_ea + al((size_t)slab_pad * 4);
+  const size_t a_one = al(a_bytes) + al((size_t)slab_pad * 8) + al((size_t)slab_pad * 4);   // digits, scales, exponents
+  const size_t off_a = al(b_bytes), off_sb = off_a + nbuf * a_one, off_eb = off_sb + al((size_t)ppad * 8),
+               total = off_eb + al((size_t)ppad * 4);
   MB_TRY(ensure_ws(ctx, total));
   unsigned char* ws = reinterpret_cast<unsigned char*>(ctx->i8_ws);
   int8_t* Bd = reinterpret_cast<int8_t*>(ws);
-  int8_t* Ad = reinterpret_cast<int8_t*>(ws + off_a);
   double* sb = reinterpret_cast<double*>(ws + off_sb);
-  double* sa = reinterpret_cast<double*>(ws + off_sa);
   int* eb = reinterpret_cast<int*>(ws + off_eb);
-  int* ea = reinterpret_cast<int*>(ws + off_ea);
 
+  if (ahead) MB_TRY(side_fork(ctx));                        // A is complete on the main stream here
+  cudaStream_t ps = ahead ? ctx->i8_side : ctx->stream;
   MB_LAUNCH(ctx, rowmax_kernel, (unsigned)ceil_div64(ppad, 8), 256, 0, B, p, k, ldb, eb, sb, ppad, ctx->i8_status);
   MB_LAUNCH(ctx, (pack_rows_kernel<TB>), dim3((unsigned)npb, (unsigned)nks), 2 * TB, 0, B, p, k, ldb, nks, eb, Bd);
-  for (int64_t r0 = 0; r0 < n; r0 += SLAB) {
+  int slab = 0;
+  for (int64_t r0 = 0; r0 < n; r0 += SLAB, slab++) {
     const int64_t rows = std::min(SLAB, n - r0), npa = ceil_div64(rows, TA), rpad = npa * TA;
-    MB_LAUNCH(ctx, rowmax_kernel, (unsigned)ceil_div64(rpad, 8), 256, 0, A + r0 * lda, rows, k, lda, ea, sa, rpad,
-              ctx->i8_status);
-    MB_LAUNCH(ctx, (pack_rows_kernel<TA>), dim3((unsigned)npa, (unsigned)nks), 2 * TA, 0, A + r0 * lda, rows, k, lda, nks, ea,
-              Ad);
+    const int buf = ahead ? (slab & 1) : 0;
+    unsigned char* wa = ws + off_a + (size_t)buf * a_one;
+    int8_t* Ad = reinterpret_cast<int8_t*>(wa);
+    double* sa = reinterpret_cast<double*>(wa + al(a_bytes));
+    int* ea = reinterpret_cast<int*>(wa + al(a_bytes) + al((size_t)slab_pad * 8));
+    if (ahead && slab >= 2) MB_CUDA(cudaStreamWaitEvent(ps, ctx->i8_ev_free[buf], 0));      // its last reader is done
+    MB_LAUNCH_ON(ctx, ps, rowmax_kernel, (unsigned)ceil_div64(rpad, 8), 256, 0, A + r0 * lda, rows, k, lda, ea, sa, rpad,
+                 ctx->i8_status);
+    MB_LAUNCH_ON(ctx, ps, (pack_rows_kernel<TA>), dim3((unsigned)npa, (unsigned)nks), 2 * TA, 0, A + r0 * lda, rows, k, lda, nks,
+                 ea, Ad);
+    if (ahead) {
+      MB_CUDA(cudaEventRecord(ctx->i8_ev_packed[buf], ps));
+      MB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->i8_ev_packed[buf], 0));
+    }
     NtArgs na;
     na.Ad = Ad;
     na.Bd = Bd;
@@ -687,6 +827,7 @@ int mb_i8_gemm_nt(mb_ctx* ctx, int64_t n, int64_t p, int64_t k, double alpha, co
     else if (ctx->opt_i8_issuers == 1) MB_LAUNCH_P(ctx, MB_PROF_I8, gemm_nt_i8_kernel<1>, ngrid, NT, SMEM_TOTAL, na);
     else if (ctx->opt_i8_issuers == 2) MB_LAUNCH_P(ctx, MB_PROF_I8, gemm_nt_i8_kernel<2>, ngrid, NT, SMEM_TOTAL, na);
     else MB_LAUNCH_P(ctx, MB_PROF_I8, gemm_nt_i8_kernel<4>, ngrid, NT, SMEM_TOTAL, na);
+    if (ahead) MB_CUDA(cudaEventRecord(ctx->i8_ev_free[buf], ctx->stream));
   }
   return 0;
 }

@@ -175,6 +175,11 @@ int mb_gemm_tn_cells(mb_ctx* ctx, const mb_chunks& g, int64_t m, int64_t n, cons
   for (int s = nbuf - 1; s >= 0; s--) pool.free_slots.push_back(s);
 
   // local phase: every own node is the tree over its leaves
+  struct SeqGuard {                          // closes the leaf sequence on every way out
+    mb_ctx* c;
+    ~SeqGuard() { mb_i8_gram_end(c); }
+  } seq_guard = {ctx};
+  if (i8) MB_TRY(mb_i8_gram_begin(ctx));     // A is complete on the stream: the leaves may pack ahead of their MMA kernels
   for (Node& nd : mine) {
     std::vector<Node> st;
     for (int c = nd.start; c < nd.start + nd.size; c++) {
@@ -196,6 +201,7 @@ int mb_gemm_tn_cells(mb_ctx* ctx, const mb_chunks& g, int64_t m, int64_t n, cons
     MB_CHECK(st.size() == 1, "mb_gemm_tn_cells: local tree did not close");
     nd.buf = st[0].buf;
   }
+  mb_i8_gram_end(ctx);
 
   // global phase: all ranks walk the canonical nodes of every rank in order; the owner broadcasts its node
   std::vector<Node> st;

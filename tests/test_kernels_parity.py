@@ -487,6 +487,36 @@ def test_gram_on_int8_digit_slices(be, n, r):
     assert rel_err(z0, O.ridge_normal_equations(L, t)) < 1e-8
 
 
+def test_int8_packs_on_the_side_stream_give_identical_bits(be):
+    """The digit pack of the next slab (TRSM updates, > 65536 rows) / chunk (Gram) runs on a side stream under the MMA
+    kernel of the current one with ``mb_set_option("i8_overlap", 1)``: same kernels on the same data, so the bits are
+    those of the one-stream sequence (the default), run after run, and the solve is right."""
+    if be.name != "cuda":
+        pytest.skip("the int8 digit-slice path exists in the CUDA library only")
+    rng = np.random.default_rng(11)
+    n, m = 140003, 640                                    # three slabs of rows, updates with k = 384 and k = 256... on int8
+    Lp = np.linalg.cholesky(_spd(m, m, 1e4))
+    X = rng.standard_normal((n, m)) * 10.0 ** rng.uniform(-4, 2, size=(n, 1))
+    Lpd = be.upload(Lp)
+    outs, grams = [], []
+    for overlap in (1, 0, 1):
+        be.set_option("i8_overlap", overlap)
+        try:
+            Xd = be.upload(X.copy(), sharded=True)
+            Ld = be.trsm_right_lt(Lpd, Xd)
+            outs.append(Ld.numpy())
+            grams.append(be.gram(Ld).numpy())
+        finally:
+            be.set_option("i8_overlap", 0)
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    assert np.array_equal(grams[0], grams[1]) and np.array_equal(grams[0], grams[2])
+    ref = solve_triangular(Lp, X.T, lower=True).T
+    rownorm = np.max(np.abs(ref), axis=1, keepdims=True)
+    assert np.max(np.abs(outs[0] - ref) / rownorm) < 1e-11
+    bound = np.abs(outs[0]).T @ np.abs(outs[0])
+    assert np.max(np.abs(grams[0] - outs[0].T @ outs[0]) / bound) < 2e-14
+
+
 def test_gram_int8_rejects_non_finite_operands(be):
     L = np.random.default_rng(0).random((65536, 512))
     L[70, 3] = np.inf
