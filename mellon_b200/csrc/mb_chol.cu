@@ -507,11 +507,11 @@ int mb_trsm_ws(mb_ctx* ctx, int64_t m) {
     MB_CUDA(mb_dev_malloc(ctx, (void**)&ctx->trsm_ws, need));
     ctx->trsm_ws_bytes = need;
   }
-  static bool configured = false;
-  if (!configured) {
+  static mb_per_device_flag configured;
+  if (!configured(ctx)) {
     MB_CUDA(cudaFuncSetAttribute(tri_inv_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IB_SMEM));
     MB_CUDA(cudaFuncSetAttribute(potrf_inv_leaf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IB_SMEM));
-    configured = true;
+    configured(ctx) = true;
   }
   return 0;
 }
@@ -730,10 +730,10 @@ extern "C" int mb_tri_solve(mb_ctx* ctx, const mb_mat* Lp, int trans, mb_mat* B)
   }
   const size_t smem = (size_t)m * sizeof(double);
   if (nrhs <= 64 && smem <= 200 * 1024) {
-    static bool configured = false;
-    if (!configured) {
+    static mb_per_device_flag configured;
+    if (!configured(ctx)) {
       MB_CUDA(cudaFuncSetAttribute(trsv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
+      configured(ctx) = true;
     }
     MB_LAUNCH(ctx, trsv_kernel, (int)nrhs, 1024, smem, Lp->p, Lp->cols, (int)m, B->p, (int)nrhs, trans);
     return 0;

@@ -179,6 +179,13 @@ void mb_set_error(const char* fmt, ...);
     MB_CUDA(cudaGetLastError());                                                   \
   } while (0)
 
+// cudaFuncSetAttribute applies to the CURRENT device: one flag per (call site, device), so that contexts on several
+// devices of one process each configure their kernels
+struct mb_per_device_flag {
+  bool done[64] = {};
+  bool& operator()(const mb_ctx* c) { return done[c->device & 63]; }
+};
+
 // launch on another stream of the context (the int8 side stream)
 #define MB_LAUNCH_ON(ctx, strm, kernel, grid, block, smem, ...)                   \
   do {                                                                             \

@@ -865,11 +865,11 @@ int launch_fast(mb_ctx* ctx, const Plan& plan, int64_t n, int64_t m, double* out
   const int prof_cls = prof_class<MODE>(ctx, plan, n, m);
 #define MB_COV_CASE(K)                                                                                        \
   case K: {                                                                                                   \
-    static bool cfg = false;                                                                                  \
-    if (!cfg) {                                                                                               \
+    static mb_per_device_flag cfg;                                                                                     \
+    if (!cfg(ctx)) {                                                                                               \
       MB_CUDA(cudaFuncSetAttribute(cov_tile_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                    200 * 1024));                                                              \
-      cfg = true;                                                                                             \
+      cfg(ctx) = true;                                                                                             \
     }                                                                                                         \
     MB_LAUNCH_P(ctx, prof_cls, (cov_tile_kernel<K, MODE>), grid, NT, smem, xo.p, xo.norm, n, yo.p, yo.norm, m, ldp, par,  \
               out, ldo, w, mu);                                                                               \
@@ -906,11 +906,11 @@ int launch_mma(mb_ctx* ctx, const Plan& plan, int64_t n, int64_t m, double* out,
   const int prof_cls = prof_class<MODE>(ctx, plan, n, m);
 #define MB_MMA_CASE(K)                                                                                       \
   case K: {                                                                                                  \
-    static bool cfg = false;                                                                                 \
-    if (!cfg) {                                                                                              \
+    static mb_per_device_flag cfg;                                                                                    \
+    if (!cfg(ctx)) {                                                                                              \
       MB_CUDA(cudaFuncSetAttribute(cov_mma_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                    200 * 1024));                                                             \
-      cfg = true;                                                                                            \
+      cfg(ctx) = true;                                                                                            \
     }                                                                                                        \
     MB_LAUNCH_P(ctx, prof_cls, (cov_mma_kernel<K, MODE>), grid, MNT, smem, xo.p, xo.norm, n, yo.p, yo.norm, m, ldp, \
                 plan.eps_scaled, out, ldo, w, mu);                                                           \
@@ -1139,11 +1139,11 @@ extern "C" int mb_nn_distances(mb_ctx* ctx, const mb_mat* x, const mb_mat* all, 
         mb_set_error("mb_nn_distances: %lld features are too many for the tile kernel", (long long)x->cols);
         rc = -2;
       } else {
-        static bool cfg = false;
-        if (!cfg) {
+        static mb_per_device_flag cfg;   
+        if (!cfg(ctx)) {
           cudaFuncSetAttribute(cov_tile_kernel<MB_K_DISTANCE, MODE_NNMIN>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-          cfg = true;
+          cfg(ctx) = true;
         }
         int grid = (int)min(ceil_div64(n, BM), (int64_t)ctx->n_sm);
         cov_tile_kernel<MB_K_DISTANCE, MODE_NNMIN><<<grid, NT, smem, ctx->stream>>>(

@@ -409,10 +409,10 @@ cov_i8_kernel(const CovI8Args a) {
 
 template <int KIND, int MODE>
 int launch_cov_i8(mb_ctx* ctx, const CovI8Args& a, size_t smem) {
-  static bool configured = false;
-  if (!configured) {
+  static mb_per_device_flag configured;
+  if (!configured(ctx)) {
     MB_CUDA((cudaFuncSetAttribute(cov_i8_kernel<KIND, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
-    configured = true;
+    configured(ctx) = true;
   }
   const int64_t n_panels = ceil_div64(a.n, TM);
   const int grid = (int)std::min<int64_t>(n_panels, ctx->n_sm);

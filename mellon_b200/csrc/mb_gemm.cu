@@ -376,12 +376,12 @@ int launch_gemm(mb_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, cons
               lower_only ? 1 : 0, tn, nt);
     return 0;
   }
-  static bool configured = false;
-  if (!configured) {
+  static mb_per_device_flag configured;
+  if (!configured(ctx)) {
     MB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<AK, BK, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     MB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<AK, BK, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     MB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<AK, BK, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    configured = true;
+    configured(ctx) = true;
   }
   int64_t tm = ceil_div64(m, BM), tn = ceil_div64(n, BN);
   int64_t nt = lower_only ? tm * (tm + 1) / 2 : tm * tn;

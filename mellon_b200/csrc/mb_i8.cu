@@ -657,13 +657,13 @@ int mb_i8_gram_leaf(mb_ctx* ctx, const double* A, int64_t lda, int64_t rows, int
     MB_CUDA(cudaMalloc(&ctx->i8_status, sizeof(int)));
     MB_CUDA(cudaMemset(ctx->i8_status, 0, sizeof(int)));
   }
-  static bool configured = false;
-  if (!configured) {
+  static mb_per_device_flag configured;
+  if (!configured(ctx)) {
     MB_CUDA(cudaFuncSetAttribute(gram_i8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     MB_CUDA(cudaFuncSetAttribute(gram_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     MB_CUDA(cudaFuncSetAttribute(gram_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     MB_CUDA(cudaFuncSetAttribute(gram_i8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    configured = true;
+    configured(ctx) = true;
   }
   // workspace: one operand buffer {digits (A and B layouts), scales, column maxima} (two inside a sequence with the
   // packs on the side stream) + per-group partial products
@@ -760,13 +760,13 @@ int mb_i8_gemm_nt(mb_ctx* ctx, int64_t n, int64_t p, int64_t k, double alpha, co
     MB_CUDA(cudaMalloc(&ctx->i8_status, sizeof(int)));
     MB_CUDA(cudaMemset(ctx->i8_status, 0, sizeof(int)));
   }
-  static bool configured = false;
-  if (!configured) {
+  static mb_per_device_flag configured;
+  if (!configured(ctx)) {
     MB_CUDA(cudaFuncSetAttribute(gemm_nt_i8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     MB_CUDA(cudaFuncSetAttribute(gemm_nt_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     MB_CUDA(cudaFuncSetAttribute(gemm_nt_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     MB_CUDA(cudaFuncSetAttribute(gemm_nt_i8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    configured = true;
+    configured(ctx) = true;
   }
   const int64_t SLAB = 65536;
   const int64_t nks = ceil_div64(k, KS), npb = ceil_div64(p, TB), ppad = npb * TB;

@@ -558,10 +558,10 @@ int launch_rowdot(mb_ctx* ctx, const mb_mat* L, const double* zdev, double mu, c
   grid = max(grid, 1);
   size_t smem = (size_t)L->cols * sizeof(double);
   MB_CHECK(smem <= 160 * 1024, "rank %lld too large for the row-dot kernel (max 20480)", (long long)L->cols);
-  static bool configured[3] = {false, false, false};
-  if (!configured[MODE]) {
+  static mb_per_device_flag configured[3];
+  if (!configured[MODE](ctx)) {
     MB_CUDA(cudaFuncSetAttribute(rowdot_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured[MODE] = true;
+    configured[MODE](ctx) = true;
   }
   MB_LAUNCH(ctx, rowdot_kernel<MODE>, grid, ROW_THREADS, smem, L->p, L->rows, (int)L->cols, zdev, mu, V, out, lv);
   return 0;
@@ -625,13 +625,13 @@ int launch_stream(mb_ctx* ctx, const mb_mat* L, const double* zdev, double mu, c
   const bool hold = (rb == 1 && cp <= 6);  // row copy in registers: 4 * cp more registers
 #define MB_STREAM(CPV)                                                                                      \
   case CPV: {                                                                                               \
-    static bool cfg = false;                                                                                \
-    if (!cfg) {                                                                                             \
+    static mb_per_device_flag cfg;                                                                                   \
+    if (!cfg(ctx)) {                                                                                             \
       MB_CUDA(cudaFuncSetAttribute(stream_rows_kernel<CPV, SQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    (int)budget));                                                           \
       MB_CUDA(cudaFuncSetAttribute(stream_rows_kernel<CPV, SQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    (int)budget));                                                           \
-      cfg = true;                                                                                           \
+      cfg(ctx) = true;                                                                                           \
     }                                                                                                       \
     if (ctx->prof_on) ctx->prof_work[MB_PROF_LOSSGRAD] += 8.0 * ((double)n * r + (double)n);                \
     if (hold) {                                                                                             \
