@@ -83,3 +83,28 @@ def test_library_is_built_from_the_sources_in_the_tree():
     assert lib.mb_source_hash().decode() == nat.source_hash()
     mk = open(os.path.join(os.path.dirname(nat.__file__), "csrc", "Makefile")).read()
     assert re.search(r"^SRCS := (.*)$", mk, re.M).group(1).split() == nat.SOURCES
+
+
+def test_product_kernels_contain_the_blackwell_instructions():
+    """The library that ships (not a prototype) runs its contractions on tcgen05: the int8 digit-slice GEMMs and K1 hold
+    UTCIMMA (tcgen05.mma kind::i8), LDTM (tcgen05.ld) and UBLKCP (bulk TMA copies); K5 streams L with UBLKCP; the FP64
+    remainder is DMMA.  Counted from the SASS of the built library (tools/sass_summary.py; no GPU needed)."""
+    import shutil
+    import sys
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump is not installed")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import sass_summary
+    finally:
+        sys.path.pop(0)
+    per, total = sass_summary.summarise(os.path.join(ROOT, "mellon_b200", "libmellon_b200.so"))
+    for kernel in ("gram_i8_kernel<4>", "gemm_nt_i8_kernel<4>", "cov_i8_kernel<1, 0>", "cov_i8_kernel<6, 1>"):
+        c = per[kernel]
+        assert c["UTCIMMA"] == 28 and c["LDTM"] >= 7 and c["UBLKCP"] >= 1, (kernel, dict(c))
+    assert per["gram_i8_kernel<0>"]["UTCCP"] == 7                      # the A-in-TMEM variant stages 7 slices by tcgen05.cp
+    k5 = [n for n in per if n.startswith("stream_rows_kernel")]
+    assert k5 and all(per[n]["UBLKCP"] >= 1 for n in k5)
+    assert any(per[n]["DMMA"] > 0 for n in per if n.startswith("gemm_dmma_kernel"))
+    assert total["UTCIMMA"] >= 13 * 28
