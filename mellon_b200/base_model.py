@@ -11,41 +11,15 @@ from __future__ import annotations
 import logging
 
 from .cov import Matern52
-from .inference import (
-    DEFAULT_INIT_LEARN_RATE,
-    DEFAULT_JIT,
-    DEFAULT_N_ITER,
-    DEFAULT_OPTIMIZER,
-    compute_laplace_std,
-    minimize_adam,
-    run_advi,
-    minimize_lbfgsb,
-)
+from .inference import (DEFAULT_INIT_LEARN_RATE, DEFAULT_JIT, DEFAULT_N_ITER, DEFAULT_OPTIMIZER, compute_laplace_std,
+                        minimize_adam, run_advi, minimize_lbfgsb)
 from .parameter_validation import validate_cov_func, validate_cov_func_curry, validate_params
-from .parameters import (
-    DEFAULT_RANDOM_SEED,
-    compute_cov_func,
-    compute_gp_type,
-    compute_L,
-    compute_landmarks,
-    compute_Lp,
-    compute_ls,
-    compute_n_landmarks,
-    compute_nn_distances,
-    compute_rank,
-)
+from .parameters import (DEFAULT_RANDOM_SEED, compute_cov_func, compute_gp_type, compute_L, compute_landmarks,
+                         compute_Lp, compute_ls, compute_n_landmarks, compute_nn_distances, compute_rank)
 from .util import DEFAULT_JITTER, GaussianProcessType, object_str, test_rank
-from .validation import (
-    validate_array,
-    validate_bool,
-    validate_float,
-    validate_float_or_int,
-    validate_float_or_iterable_numerical,
-    validate_nn_distances,
-    validate_positive_float,
-    validate_positive_int,
-    validate_string,
-)
+from .validation import (validate_array, validate_bool, validate_float, validate_float_or_int,
+                         validate_float_or_iterable_numerical, validate_nn_distances, validate_positive_float,
+                         validate_positive_int, validate_string)
 
 DEFAULT_COV_FUNC = Matern52
 RANK_FRACTION_THRESHOLD = 0.8

@@ -22,17 +22,32 @@ from __future__ import annotations
 import logging
 
 from .base_model import DEFAULT_COV_FUNC, BaseEstimator
-from .inference import (
-    DEFAULT_INIT_LEARN_RATE,
-    DEFAULT_N_ITER,
-    DEFAULT_OPTIMIZER,
-    compute_conditional,
-)
+from . import inference as I
+from . import validation as V
+from .inference import DEFAULT_INIT_LEARN_RATE, DEFAULT_N_ITER, DEFAULT_OPTIMIZER
 from .parameters import DEFAULT_RANDOM_SEED
 from .util import DEFAULT_JITTER, GaussianProcessType, object_html
-from .validation import validate_array, validate_bool, validate_float, validate_float_or_iterable_numerical
 
 logger = logging.getLogger("mellon")
+
+NYSTROEM_TYPES = (GaussianProcessType.FULL_NYSTROEM, GaussianProcessType.SPARSE_NYSTROEM)
+# message text of the reference (function_estimator.py:171-177, 350-355, 399-403, 545-560, 598-609)
+MSG_NO_NYSTROEM = ("gp_type={gp_type} but the Nyström rank reduction is "
+                   "not available for the Function Estimator. "
+                   "Use gp_type='cholesky' or gp_type='full' instead.")
+MSG_OTHER_X = ("self.x has been set already, but is not equal to the argument x. "
+               "Current landmarks might be inapropriate.")
+MSG_SAMPLES = "X.shape[0] = {n:,} (n_samples) should equal y.shape[0] = {m:,}."
+MSG_NDIM = ("The provided arrays, 'x' and 'Xnew', do not have the same number of dimensions. "
+            "'x' is {a}-D and 'Xnew' is {b}-D. Please provide arrays with consistent dimensionality.")
+MSG_FEATURES = ("The provided arrays, 'x' and 'Xnew', should have the same number of features. "
+                "Got Xnew.shape[1] = {b}, but expected it to be equal to x.shape[1] = {a}. "
+                "Please provide arrays with the same number of features.")
+MSG_DEPRECATED = ("Deprecation Warning: FunctionEstimator's multi_fit_predict method is deprecated. "
+                  "Use FunctionEstimator.fit_reodict instead.")
+MSG_TRANSPOSE = ("Y.shape[0] does not equal X.shape[0] (the number of samples). "
+                 "However, Y.shape[1] == X.shape[0]. Transposing Y. "
+                 "This assumes the columns of Y are the samples. Please verify.")
 
 
 class FunctionEstimator(BaseEstimator):
@@ -48,18 +63,11 @@ class FunctionEstimator(BaseEstimator):
             landmarks=landmarks, nn_distances=nn_distances, mu=mu, ls=ls, ls_factor=ls_factor, cov_func=cov_func,
             predictor_with_uncertainty=predictor_with_uncertainty, jit=jit, random_state=random_state,
         )
-        self.y_is_mean = validate_bool(y_is_mean, "y_is_mean")
-        self.mu = validate_float(mu, "mu")
-        self.sigma = validate_float_or_iterable_numerical(sigma, "sigma", positive=True)
-        self.obs_variance = validate_bool(obs_variance, "obs_variance")
-        if self.gp_type in (GaussianProcessType.FULL_NYSTROEM, GaussianProcessType.SPARSE_NYSTROEM):
-            message = (
-                f"gp_type={gp_type} but the Nyström rank reduction is "
-                "not available for the Function Estimator. "
-                "Use gp_type='cholesky' or gp_type='full' instead."
-            )
-            logger.error(message)
-            raise ValueError(message)
+        self.y_is_mean, self.obs_variance = V.validate_bool(y_is_mean, "y_is_mean"), V.validate_bool(obs_variance, "obs_variance")
+        self.mu = V.validate_float(mu, "mu")
+        self.sigma = V.validate_float_or_iterable_numerical(sigma, "sigma", positive=True)
+        if self.gp_type in NYSTROEM_TYPES:
+            self._fail(MSG_NO_NYSTROEM.format(gp_type=gp_type))
 
     def __call__(self, x=None, y=None):
         """``fit_predict(x, y)`` (``function_estimator.py:180-192``)."""
@@ -70,15 +78,10 @@ class FunctionEstimator(BaseEstimator):
         return text[:-2] + f"\n    sigma={self.sigma},\n    y_is_mean={self.y_is_mean},\n)"
 
     def _repr_html_(self):
-        rows = {
-            "Jitter": self.jitter,
-            "Mean (μ)": self.mu or "Not Set",
-            "Length Scale (ls)": self.ls or "Not Set",
-            "Length-Scale Factor": self.ls_factor,
-            "Noise Standard Deviation (σ)": self.sigma,
-            "y_is_mean": self.y_is_mean,
-            "Nearest Neighbor Distances": self.nn_distances,
-        }
+        unset = "Not Set"
+        rows = {"Jitter": self.jitter, "Mean (μ)": self.mu or unset, "Length Scale (ls)": self.ls or unset,
+                "Length-Scale Factor": self.ls_factor, "Noise Standard Deviation (σ)": self.sigma,
+                "y_is_mean": self.y_is_mean, "Nearest Neighbor Distances": self.nn_distances}
         table = "".join(f"<tr><td>{k}</td><td>{object_html(v)}</td></tr>" for k, v in rows.items())
         status = "Available" if getattr(self, "conditional", None) else "Not Yet Computed"
         return (
@@ -92,50 +95,33 @@ class FunctionEstimator(BaseEstimator):
     def prepare_inference(self, x):
         """Fill n_landmarks, gp_type, (nn_distances,) ls, cov_func and landmarks
         (``function_estimator.py:295-316``)."""
-        x = self.set_x(x)
-        self._prepare_attribute("n_landmarks")
-        self._prepare_attribute("gp_type")
-        if self.ls is None and self.cov_func is None:
-            self._prepare_attribute("nn_distances")
-        self._prepare_attribute("ls")
-        self._prepare_attribute("cov_func")
-        self._prepare_attribute("landmarks")
+        self.set_x(x)
+        needs_distances = self.ls is None and self.cov_func is None     # only the length-scale heuristic reads them
+        for name in ("n_landmarks", "gp_type", "nn_distances", "ls", "cov_func", "landmarks"):
+            if name != "nn_distances" or needs_distances:
+                self._prepare_attribute(name)
 
     def compute_conditional(self, x=None, y=None, obs_variance=None):
         """Condition the GP on ``y`` observed at ``x`` (``function_estimator.py:318-374``)."""
-        given = x
+        given, x = x, (self.x if x is None else V.validate_array(x, "x"))
         if x is None:
-            x = self.x
-        else:
-            x = validate_array(x, "x")
-        if self.x is not None and self.x is not x and self._x_given is not given:
-            logger.warning(
-                "self.x has been set already, but is not equal to the argument x. "
-                "Current landmarks might be inapropriate."
-            )
-        if self.x is None and x is None:
             raise ValueError("Required argument x is missing and self.x has not been set.")
+        if self.x is not None and self.x is not x and self._x_given is not given:
+            logger.warning(MSG_OTHER_X)
         if y is None:
             raise ValueError("Required argument y is missing.")
-        if obs_variance is None:
-            obs_variance = self.obs_variance
-        conditional = compute_conditional(
+        self.conditional = I.compute_conditional(
             x, self.landmarks, None, None, y, self.mu, self.cov_func, None, None, self.sigma, jitter=self.jitter,
-            y_is_mean=self.y_is_mean, with_uncertainty=self.predictor_with_uncertainty, obs_variance=obs_variance,
+            y_is_mean=self.y_is_mean, with_uncertainty=self.predictor_with_uncertainty,
+            obs_variance=self.obs_variance if obs_variance is None else obs_variance,
         )
-        self.conditional = conditional
-        return conditional
+        return self.conditional
 
     def fit(self, x=None, y=None, obs_variance=None):
         """Prepare the covariance and landmarks, then condition on ``y`` (``function_estimator.py:376-420``)."""
-        x = self.set_x(x)
-        y = validate_array(y, "y")
-        n_samples = x.shape[0]
-        if y.shape[0] != n_samples:
-            raise ValueError(
-                f"X.shape[0] = {n_samples:,} (n_samples) should equal "
-                f"y.shape[0] = {y.shape[0]:,}."
-            )
+        x, y = self.set_x(x), V.validate_array(y, "y")
+        if y.shape[0] != x.shape[0]:
+            raise ValueError(MSG_SAMPLES.format(n=x.shape[0], m=y.shape[0]))
         self.prepare_inference(x)
         self.compute_conditional(x, y, obs_variance=obs_variance)
         self.y = y
@@ -170,40 +156,20 @@ class FunctionEstimator(BaseEstimator):
     def fit_predict(self, x=None, y=None, Xnew=None):
         """Fit, then return the conditional mean at ``Xnew`` (default: ``x``), one column per column of ``y``
         (``function_estimator.py:507-565``)."""
-        x = self.set_x(x)
-        y = validate_array(y, "y")
-        Xnew = validate_array(Xnew, "Xnew", optional=True)
-        if Xnew is None:
-            Xnew = x
-        else:
-            if x.ndim != Xnew.ndim:
-                raise ValueError(
-                    f"The provided arrays, 'x' and 'Xnew', do not have the same number of dimensions. "
-                    f"'x' is {x.ndim}-D and 'Xnew' is {Xnew.ndim}-D. Please provide arrays with consistent dimensionality."
-                )
-            if x.ndim > 1 and x.shape[1] != Xnew.shape[1]:
-                raise ValueError(
-                    f"The provided arrays, 'x' and 'Xnew', should have the same number of features. "
-                    f"Got Xnew.shape[1] = {Xnew.shape[1]}, but expected it to be equal to x.shape[1] = {x.shape[1]}. "
-                    "Please provide arrays with the same number of features."
-                )
+        x, y = self.set_x(x), V.validate_array(y, "y")
+        Xnew = V.validate_array(Xnew, "Xnew", optional=True)
+        if Xnew is not None and Xnew.ndim != x.ndim:
+            raise ValueError(MSG_NDIM.format(a=x.ndim, b=Xnew.ndim))
+        if Xnew is not None and x.ndim > 1 and Xnew.shape[1] != x.shape[1]:
+            raise ValueError(MSG_FEATURES.format(a=x.shape[1], b=Xnew.shape[1]))
         self.fit(x, y)
-        return self.predict(Xnew)
+        return self.predict(x if Xnew is None else Xnew)
 
     def multi_fit_predict(self, x=None, Y=None, Xnew=None):
         """Deprecated row-per-output form of :meth:`fit_predict` (``function_estimator.py:567-615``)."""
-        logger.warning(
-            "Deprecation Warning: FunctionEstimator's multi_fit_predict method is deprecated. "
-            "Use FunctionEstimator.fit_reodict instead."
-        )
-        x = self.set_x(x)
-        Y = validate_array(Y, "Y")
-        n_samples = x.shape[0]
-        if Y.shape[0] != n_samples and Y.shape[1] == n_samples:
-            logger.warning(
-                "Y.shape[0] does not equal X.shape[0] (the number of samples). "
-                "However, Y.shape[1] == X.shape[0]. Transposing Y. "
-                "This assumes the columns of Y are the samples. Please verify."
-            )
+        logger.warning(MSG_DEPRECATED)
+        x, Y = self.set_x(x), V.validate_array(Y, "Y")
+        if Y.shape[0] != x.shape[0] and Y.shape[1] == x.shape[0]:
+            logger.warning(MSG_TRANSPOSE)
             Y = Y.T
         return self.fit_predict(x, Y, Xnew).T

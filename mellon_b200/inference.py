@@ -18,14 +18,8 @@ from scipy.optimize import minimize
 from scipy.special import gammaln
 
 from .backend import DeviceArray, get_backend
-from .conditional import (
-    FullConditional,
-    FullConditionalTime,
-    LandmarksConditional,
-    LandmarksConditionalCholesky,
-    LandmarksConditionalCholeskyTime,
-    LandmarksConditionalTime,
-)
+from .conditional import (FullConditional, FullConditionalTime, LandmarksConditional, LandmarksConditionalCholesky,
+                          LandmarksConditionalCholeskyTime, LandmarksConditionalTime)
 from .util import DEFAULT_JITTER, ensure_2d
 
 logger = logging.getLogger("mellon")

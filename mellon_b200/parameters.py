@@ -13,25 +13,12 @@ import logging
 import numpy as np
 
 from .backend import DeviceArray, get_backend
-from .decomposition import (
-    DEFAULT_RANK,
-    DEFAULT_SIGMA,
-    _full_decomposition_low_rank,
-    _full_rank,
-    _modified_low_rank,
-    _standard_low_rank,
-)
+from .decomposition import (DEFAULT_RANK, DEFAULT_SIGMA, _full_decomposition_low_rank, _full_rank, _modified_low_rank,
+                            _standard_low_rank)
 from .parameter_validation import validate_normalize_parameter, validate_params
 from .util import DEFAULT_JITTER, GaussianProcessType, ensure_2d, mle
-from .validation import (
-    validate_array,
-    validate_float_or_int,
-    validate_float_or_iterable_numerical,
-    validate_k,
-    validate_positive_float,
-    validate_positive_int,
-    validate_time_x,
-)
+from .validation import (validate_array, validate_float_or_int, validate_float_or_iterable_numerical, validate_k,
+                         validate_positive_float, validate_positive_int, validate_time_x)
 
 DEFAULT_N_LANDMARKS = 5000
 DEFAULT_RANDOM_SEED = 42
